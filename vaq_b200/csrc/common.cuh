@@ -1,0 +1,211 @@
+// Shared device/host definitions for the vaqgpu kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vaqgpu {
+
+constexpr int kMaxSubspaces = 128;   // M
+constexpr int kMaxRowWords = 32;     // 32-bit words per packed row (<= 1024 bits)
+constexpr int kTileRows = 32;        // rows per tile == warp width
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+// fmeta bit layout: [4:0] shift inside the starting 32-bit word, [5] table spilled to
+// global/L2, [31:16] value mask ((1<<bits)-1).
+constexpr uint32_t kFieldSpill = 1u << 5;
+
+// Where each subspace code sits in the packed row, and where its LUT lives.
+// Rows are little-endian bit strings: subspace s occupies bits [bitoff_s, bitoff_s+bits_s),
+// bitoff_s = sum_{t<s} bits_t; bit i lives in 32-bit word i/32 at position i%32.
+struct ScanLayout {
+  int32_t M;                          // subspaces
+  int32_t W;                          // uint4 words per row
+  uint16_t fbeg[kMaxRowWords + 1];    // fields starting in word w: [fbeg[w], fbeg[w+1])
+  uint32_t fmeta[kMaxSubspaces];      // see above
+  uint32_t foff[kMaxSubspaces];       // float offset of table s inside the smem LUT or the spill area
+};
+
+// Where the LUT build kernel writes table s inside a query's LUT row.
+struct LutPlan {
+  int32_t M, L;
+  int32_t total_entries;              // sum K_s
+  int32_t row_stride;                 // floats per query row in the LUT workspace
+  int32_t ent_off[kMaxSubspaces + 1]; // compact entry offsets (prefix sum of K_s)
+  int32_t pos[kMaxSubspaces];         // float position of table s in the workspace row
+  int32_t cent_off[kMaxSubspaces];    // float offset of centroid block s
+};
+
+__host__ __device__ inline uint64_t make_key_f32(float d, int32_t id) {
+#ifdef __CUDA_ARCH__
+  return ((uint64_t)__float_as_uint(d) << 32) | (uint32_t)id;
+#else
+  union { float f; uint32_t u; } c; c.f = d;
+  return ((uint64_t)c.u << 32) | (uint32_t)id;
+#endif
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared) -------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// bytes must be a multiple of 16, src/dst 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- per-warp sorted top-k list in shared memory --------------------------------------
+// list[0..k) ascending; insert `key` (warp-uniform) if it is smaller than list[k-1].
+// All 32 lanes must call.  Returns the (possibly new) k-th key.
+__device__ __forceinline__ uint64_t warp_list_insert(volatile uint64_t *list, int k, uint64_t key, int lane) {
+  uint64_t kth = list[k - 1];
+  if (!(key < kth)) return kth;
+  int cnt = 0;
+  for (int i = lane; i < k; i += 32) cnt += (list[i] < key) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  const int rank = cnt;
+  for (int base = ((k - 1) >> 5) << 5; base >= 0; base -= 32) {
+    const int i = base + lane;
+    uint64_t v = 0;
+    const bool mv = (i < k) && (i > rank);
+    if (mv) v = list[i - 1];
+    __syncwarp();
+    if (mv) list[i] = v;
+    else if (i == rank) list[i] = key;
+    __syncwarp();
+    if (base <= rank) break;   // everything below `rank` is unchanged
+  }
+  return list[k - 1];
+}
+
+// count of entries < key in an ascending list (binary search)
+__device__ __forceinline__ int lower_bound_u64(const uint64_t *a, int n, uint64_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Merge `nlists` ascending lists of k keys (contiguous: lists[l*k + i]) into the k smallest,
+// written ascending to out[0..k).  Keys are unique except kEmptyKey padding.  Block-collective.
+__device__ __forceinline__ void block_merge_lists(const uint64_t *lists, int nlists, int k, uint64_t *out) {
+  for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = kEmptyKey;
+  __syncthreads();
+  const int total = nlists * k;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const uint64_t key = lists[e];
+    if (key == kEmptyKey) continue;
+    const int l = e / k, i = e - l * k;
+    int rank = i;
+    for (int o = 0; o < nlists && rank < k; o++) {
+      if (o == l) continue;
+      rank += lower_bound_u64(lists + o * k, k, key);
+    }
+    if (rank < k) out[rank] = key;
+  }
+  __syncthreads();
+}
+
+#endif  // __CUDACC__
+
+// ---- launchers (one per .cu) ----------------------------------------------------------
+struct AdcScanArgs {
+  const uint4 *codes;        // packed tiles [tile][w][lane]
+  int64_t n_rows;            // valid rows
+  const float *lut;          // LUT workspace [nq][row_stride]
+  int32_t lut_stride;        // floats
+  int32_t smem_lut_floats;   // resident floats (multiple of 4)
+  int32_t nq, k, splits;
+  int32_t early_abandon;     // 1 = EA votes on
+  int32_t use_tma;           // 1 = cp.async.bulk LUT staging
+  uint64_t *out_keys;        // [nq][splits][k]; low word = LOCAL row index
+  // TI / visit mode: per-query list of row ranges (NULL = whole index)
+  const int2 *ranges;        // [nq][max_ranges] (row_begin, row_end) in visiting order
+  const int32_t *n_ranges;   // [nq]
+  int32_t max_ranges;
+  ScanLayout lay;
+};
+
+cudaError_t launch_adc_scan(const AdcScanArgs &a, int threads, size_t smem_bytes, cudaStream_t st);
+cudaError_t adc_scan_occupancy(int W, int threads, size_t smem_bytes, int *ctas_per_sm);
+
+cudaError_t launch_lut_build(const float *q_proj, int nq, int D, const float *centroids, const LutPlan &plan,
+                             float *lut, cudaStream_t st);
+cudaError_t launch_project(const float *x, int n, int D, const float *eig, float *out, cudaStream_t st);
+
+cudaError_t launch_pack_codes(const uint16_t *codes, int64_t n, int64_t row0, const ScanLayout &lay, uint4 *packed,
+                              cudaStream_t st);
+cudaError_t launch_unpack_codes(const uint4 *packed, int64_t row0, int64_t n, const ScanLayout &lay, uint16_t *codes,
+                                cudaStream_t st);
+cudaError_t launch_encode(const float *x_proj, int64_t n, const float *centroids, const LutPlan &plan,
+                          uint16_t *codes, cudaStream_t st);
+cudaError_t launch_synth_codes(uint16_t *codes, int64_t n, int64_t global_row0, int M, const int32_t *bits,
+                               const float *cdf, const int32_t *ent_off, uint64_t seed, cudaStream_t st);
+
+// List l of query q starts at keys_in + l*stride_l + q*stride_q (G ascending lists of k keys per
+// query).  Writes the k smallest per query.  Low words are remapped on output:
+// id = id_map ? id_map[low] : low + id_base.  Any of ids / dist / keys_out may be NULL.
+// `scratch` (2 * nq * ceil(G/16) * k keys) is needed only when G > 16.
+cudaError_t launch_merge_keys(const uint64_t *keys_in, int64_t stride_l, int64_t stride_q, int G, int nq, int k,
+                              int sqrt_flag, int hamming, int32_t *ids, void *dist, uint64_t *keys_out,
+                              const int32_t *id_map, int64_t id_base, uint64_t *scratch, cudaStream_t st);
+
+struct HamScanArgs {
+  const uint4 *codes;        // packed tiles [tile][w][lane]
+  int64_t n_rows;
+  int32_t W;                 // uint4 per row
+  const uint4 *queries;      // [nq][W]
+  int32_t nq, k, splits, qt; // qt = queries per CTA
+  uint64_t *out_keys;        // [nq][splits][k]; low word = LOCAL row index
+};
+cudaError_t launch_ham_scan(const HamScanArgs &a, int threads, size_t smem_bytes, cudaStream_t st);
+cudaError_t launch_ham_pack(const uint64_t *words, int64_t n, int64_t row0, int w64, int W, uint4 *packed,
+                            cudaStream_t st);
+cudaError_t launch_ham_synth(uint4 *packed, int64_t n, int64_t row0, int64_t global_row0, int nbits, int W,
+                             uint64_t seed, cudaStream_t st);
+
+cudaError_t launch_refine(const float *xtrain, int64_t n, int D, const float *queries, int nq,
+                          const int32_t *in_labels, int refine_num, int k, int32_t *labels, float *dists,
+                          cudaStream_t st);
+cudaError_t launch_rank_clusters(const float *q_proj, int nq, int D, const float *clusters, int C, int segdims,
+                                 const int64_t *start, const int64_t *size, float visit, int k, int2 *ranges,
+                                 int32_t *n_ranges, cudaStream_t st);
+
+}  // namespace vaqgpu
