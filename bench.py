@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Headline benchmark: VAQ query-time search (LUT build -> ADC scan -> top-k) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU search
+
+Workload (BASELINE.json configs[1]): SIFT1M-shape synthetic, 1M x 128 base, 10K queries,
+VAQ 256-bit budget over 32 subspaces, k = 10.  A step = one search of the whole 10K-query batch
+against the index.  N > 1 (torchrun, one rank per GPU): the code matrix is row-sharded, every
+rank scans its rows for all queries, one NCCL all-gather of the shard-local top-k + device merge
+(strong scaling: total rows fixed).
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: rows, dims, budget, M, min_bits, max_bits, queries, k, decay
+    "sift1m_256b_m32_k10": dict(n=1_000_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0),
+    "small_256b_m32_k10": dict(n=100_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=1_000, k=10, decay=4.0),
+}
+TRAIN_ROWS = 32768
+SEED = 13517106
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def build_problem(w: dict):
+    """Seeded synthetic base/queries + host-trained model (the reference keeps training on the host)."""
+    from vaq_b200 import synth, train
+    t0 = time.time()
+    X = synth.decaying_gaussian(w["n"], w["d"], decay=w["decay"], seed=SEED)
+    Qraw = synth.decaying_gaussian(w["nq"], w["d"], decay=w["decay"], seed=SEED + 7)
+    model, _ = train.train(X[:TRAIN_ROWS], w["budget"], w["M"], w["min_bits"], w["max_bits"], kmeans_iters=8, seed=SEED)
+    XP = model.project(X)
+    Q = model.project(Qraw)
+    log(f"[bench] problem built in {time.time() - t0:.1f}s bits={model.bits.tolist()}")
+    return model, X, XP, Qraw, Q
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); smax.append(float(p[1])); pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU search (compiled unmodified reference when available)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference_search(model, codes, Q, k, seconds_target: float, threads: int):
+    """Times reference VAQ::search (EA mode, the reference's fastest exact mode) on a bounded sample of
+    the query batch.  Returns (qps, n_queries, kind, labels, dists)."""
+    from oracle import oracle as orc
+    om = orc.Model(model.L, model.bits, model.centroids)
+    if orc.Ref.available():
+        kind = "reference"
+        rv = orc.Ref().vaq(om, orc.NN_EA)
+        rv.set_codes(codes)
+
+        def run(q):
+            return rv.search(q, k, nthreads=threads)
+    else:
+        kind = "port"
+        port = orc.Port()
+
+        def run(q):
+            return port.search(om, codes, q, k, "EA", nthreads=threads)
+    probe = min(Q.shape[0], max(threads, 16))
+    t0 = time.perf_counter()
+    run(Q[:probe])
+    t_probe = time.perf_counter() - t0
+    n = int(min(Q.shape[0], max(probe, seconds_target / max(t_probe / probe, 1e-9))))
+    n = max(threads, (n // threads) * threads)
+    n = min(n, Q.shape[0])
+    t0 = time.perf_counter()
+    lab, dis = run(Q[:n])
+    dt = time.perf_counter() - t0
+    return n / dt, n, kind, lab, dis, dt
+
+
+def run_reference_arm(args, w, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    model, X, XP, Qraw, Q = build_problem(w)
+    om = orc.Model(model.L, model.bits, model.centroids)
+    t0 = time.time()
+    if orc.Ref.available():      # VAQ::encode of the compiled reference (OpenMP over rows, VAQ.cpp:733)
+        rv = orc.Ref().vaq(om, orc.NN_EA)
+        codes = rv.encode(XP)
+        rv.close()
+    else:
+        codes = orc.Port().encode(om, XP)
+    log(f"[bench] host encode {time.time() - t0:.1f}s")
+    threads = os.cpu_count() or 1
+    vals = []
+    n_used = 0
+    kind = "reference"
+    per_step_target = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for it in range(args.warmup + args.steps):
+        qps, n_used, kind, _, _, dt = cpu_reference_search(model, codes, Q, w["k"], per_step_target, threads)
+        if it >= args.warmup:
+            vals.append((qps, dt))
+    qps = float(np.mean([v[0] for v in vals]))
+    ms = float(np.mean([v[1] for v in vals]) * 1e3)
+    line = {
+        "impl": "reference", "metric": "queries/sec at recall@10", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "rows": w["n"], "dims": w["d"], "queries": w["nq"], "k": w["k"], "bits": w["budget"],
+                   "subspaces": w["M"], "mode": "EA (VAQ::searchEarlyAbandon)"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind,
+                         "sample": f"{n_used} of {w['nq']} queries per step, all {w['n']} rows, query-sliced over {threads} threads"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+
+def run_gpu_arm(args, w, name):
+    import torch
+    import torch.distributed as dist
+    from vaq_b200 import synth
+    from vaq_b200.index import EA, PROJECTED, VAQIndex
+    from vaq_b200.sharded import ShardedVAQ, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log(f"[bench] WORLD_SIZE={world} overrides --gpus {args.gpus}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, X, XP, Qraw, Q = build_problem(w)
+    n, nq, k = w["n"], w["nq"], w["k"]
+    flags = EA | PROJECTED
+
+    # index: this rank's row block, encoded on the device (bit-exact vs the oracle, tests/test_gpu_vaq.py)
+    sh = ShardedVAQ(model.L, model.bits, model.centroids, model.eig, n, rank, world, local_rank)
+    t0 = time.time()
+    sh.index.encode_add(XP[sh.lo:sh.hi])
+    log(f"[bench] rank {rank}: encoded rows [{sh.lo},{sh.hi}) in {time.time() - t0:.1f}s; row_bytes={sh.index.row_bytes}")
+    ix = sh.index
+
+    d_q = torch.from_numpy(Q).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+
+    def step_device():
+        return sh.search(d_q, k, flags)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    scan_ms, lut_ms, merge_ms = [], [], []
+    launches = 0
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)            # L2 flush between timed steps (outside the per-step event bracket)
+        barrier()
+        ev[i][0].record(st)
+        labels, dists = step_device()
+        ev[i][1].record(st)
+        torch.cuda.synchronize()
+        t = ix.last_timings()
+        scan_ms.append(t["scan_ms"]); lut_ms.append(t["lut_ms"]); merge_ms.append(t["merge_ms"])
+        launches += ix.last_config()["launches"] + (1 if world > 1 else 0) + 1   # + all-gather + final merge
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev], dtype=np.float64)
+    total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = nq * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region
+    q_pin = torch.from_numpy(Q).pin_memory()
+    lab_pin = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+    dis_pin = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        if world == 1:
+            ix.search_into(q_pin.numpy(), k, flags, lab_pin.numpy(), dis_pin.numpy())     # the C-ABI host call
+        else:
+            dq = q_pin.to(dev, non_blocking=True)
+            l, d = sh.search(dq, k, flags)
+            lab_pin.copy_(l, non_blocking=True)
+            dis_pin.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_qps = nq * args.steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (ADC scan), T = 1 accounting (each query's CTAs stream the rows)
+    cfg = ix.last_config()
+    n_local = sh.hi - sh.lo
+    row_bytes = ix.row_bytes
+    lut_bytes = int(ix.lut_size) * 4
+    n_launch = -(-nq // cfg["queries_per_launch"])
+    alg_bytes_step = nq * (n_local * row_bytes + lut_bytes + k * 8 * cfg["splits"])
+    scan_ms_mean = float(np.mean(scan_ms))
+    peak, peak_src = measured_peak_hbm()
+    achieved = alg_bytes_step / (scan_ms_mean / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "adc_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
+                "launch_ms": scan_ms_mean / n_launch, "query_tile_T": 1,
+                "note": ("T=1 accounting (SURVEY 8d): every query streams all local rows; at this shape the packed codes "
+                         f"({n_local * row_bytes / 1e6:.0f} MB) are L2-resident, so DRAM traffic is far below the algorithmic bytes — "
+                         "see roofline_hbm_shape for the same kernel on a shard >> L2")}
+
+    # ---- the same kernel on a shard far larger than L2 (the HBM-bound regime of the 100M / 1B-row shapes)
+    hbm_shape = None
+    if not args.no_hbm_shape:
+        try:
+            big_n = args.hbm_rows
+            big = VAQIndex(model.L, model.bits, model.centroids, device=local_rank)
+            big.reserve(big_n)
+            cdf = synth.code_cdf(ix.get_codes(0, min(n_local, 200_000)), model.bits)
+            big.add_synthetic(big_n, SEED, cdf)
+            bq = 64
+            lab = torch.empty((bq, k), dtype=torch.int32, device=dev)
+            dis = torch.empty((bq, k), dtype=torch.float32, device=dev)
+            ms = []
+            for i in range(3 + 5):
+                big.search_device(d_q.data_ptr(), bq, k, flags, lab.data_ptr(), dis.data_ptr(), st.cuda_stream)
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ms.append(big.last_timings()["scan_ms"])
+            b = bq * (big_n * row_bytes + lut_bytes)
+            a = b / (np.mean(ms) / 1e3) / 1e9
+            hbm_shape = {"rows": big_n, "queries": bq, "packed_bytes": big_n * row_bytes, "scan_ms": float(np.mean(ms)),
+                         "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "query_tile_T": 1,
+                         "config": big.last_config()}
+            big.close()
+        except Exception as e:      # never hide the headline behind the auxiliary leg
+            hbm_shape = {"error": repr(e)}
+
+    # ---- CPU baseline on the box's host cores + parity of the returned neighbours on the same queries
+    cpu = None
+    parity = None
+    if not args.no_cpu:
+        codes_local = ix.get_codes()
+        if world == 1:
+            threads = os.cpu_count() or 1
+            qps, n_used, kind, rlab, rdis, dt = cpu_reference_search(model, codes_local, Q, k, args.cpu_seconds, threads)
+            cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind,
+                   "sample": f"{n_used} of {nq} queries, all {n} rows, EA mode, query-sliced over {threads} threads, {dt:.1f}s"}
+            glab = lab_pin.numpy()[:n_used]
+            gdis = dis_pin.numpy()[:n_used]
+            same = float((glab == rlab).mean())
+            rel = float(np.max(np.abs(gdis - rdis) / np.maximum(rdis, 1e-30)))
+            gt = synth.brute_force_knn(X, Qraw[:min(n_used, 200)], k)
+            parity = {"queries": n_used, "ids_equal_frac": same, "max_rel_dist_err": rel,
+                      "recall_at_10_gpu": synth.recall_at_k(glab[:gt.shape[0]], gt, k),
+                      "recall_at_10_reference": synth.recall_at_k(rlab[:gt.shape[0]], gt, k)}
+
+    line = {
+        "metric": "queries/sec at recall@10", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "rows": n, "dims": w["d"], "queries": nq, "k": k, "bits": w["budget"], "subspaces": w["M"],
+                   "mode": "EA", "row_bytes": row_bytes, "sharding": f"rows/{world}", "l2": "256 MB fill between timed steps",
+                   "scan_config": cfg},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(Q.nbytes), "d2h_bytes_per_step": int(nq * k * 8)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_hbm_shape": hbm_shape,
+        "cpu_baseline": cpu,
+        "parity_vs_cpu": parity,
+        "kernel_ms": {"lut_build": float(np.mean(lut_ms)), "adc_scan": scan_ms_mean, "merge": float(np.mean(merge_ms))},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sift1m_256b_m32_k10", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-hbm-shape", action="store_true")
+    ap.add_argument("--hbm-rows", type=int, default=64_000_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w, args.workload)
+    else:
+        run_gpu_arm(args, w, args.workload)
+
+
+if __name__ == "__main__":
+    main()

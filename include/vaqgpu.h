@@ -87,6 +87,9 @@ int vaqgpu_encode_add(vaqgpu_t *h, const float *x_proj, int64_t n);
  * generator is restated in numpy (vaq_b200/synth_codes.py) for CPU parity on row slices. */
 int vaqgpu_add_codes_synthetic(vaqgpu_t *h, int64_t n, uint64_t seed, const float *cdf);
 
+/* Pre-size the packed code matrix for n_total rows (avoids regrowth copies on 100M+ row shards). */
+int vaqgpu_reserve(vaqgpu_t *h, int64_t n_total);
+
 int vaqgpu_num_rows(const vaqgpu_t *h, int64_t *n);
 /* bytes per packed row in HBM (16 * ceil(sum(bits)/128)) */
 int vaqgpu_row_bytes(const vaqgpu_t *h, int32_t *bytes);

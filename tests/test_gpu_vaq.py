@@ -1,0 +1,325 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle port and the reference
+fixtures.  Integer work (codes, ids) bit-exact; distances per SURVEY Appendix B."""
+import numpy as np
+import pytest
+
+from helpers import RTOL, assert_knn_equiv, bitwise_equal, golden_model, load_golden, orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def port():
+    return orc.Port()
+
+
+def make_index(m, eig=None, codes=None):
+    from vaq_b200.index import VAQIndex
+    ix = VAQIndex(m.L, m.bits, m.centroids, eig=eig)
+    if codes is not None:
+        ix.add_codes(codes)
+    return ix
+
+
+def random_model(rng, M, L, bits):
+    cents = [rng.standard_normal((1 << b, L)).astype(np.float32) * (1.0 + 3.0 / (1 + s)) for s, b in enumerate(bits)]
+    return orc.Model(L, np.asarray(bits, np.int32), cents)
+
+
+def random_codes(rng, m, n):
+    return np.stack([rng.integers(0, 1 << int(b), size=n) for b in m.bits], 1).astype(np.uint16)
+
+
+# ---- codes ------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("bits", [
+    [8] * 16,                                  # 128 bits, byte aligned
+    [9, 9, 9, 8, 8, 7, 7, 7] * 4,              # 256 bits, straddling fields
+    [13, 11, 10, 9, 7, 5, 3, 2, 1, 15, 14, 12],  # every odd width, 102 bits -> one padded word
+    [15] * 68,                                 # 1020 bits, 8 words
+    [1] * 5,
+])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 70001])
+def test_pack_roundtrip_bit_exact(bits, n):
+    rng = np.random.default_rng(len(bits) * 1000 + n)
+    m = random_model(rng, len(bits), 1, bits)
+    codes = random_codes(rng, m, n)
+    ix = make_index(m)
+    half = n // 2
+    ix.add_codes(codes[:half])      # two appends: exercises growth + unaligned row0
+    ix.add_codes(codes[half:])
+    assert ix.num_rows == n
+    assert ix.row_bytes == 16 * ((sum(bits) + 127) // 128)
+    assert np.array_equal(ix.get_codes(), codes)
+    if n > 40:
+        assert np.array_equal(ix.get_codes(7, 30), codes[7:37])
+    ix.close()
+
+
+def test_encode_bit_exact_vs_port_and_reference(port):
+    for case in ("vaq_small_a", "vaq_small_b"):
+        g = load_golden(case)
+        m, _ = golden_model(g)
+        ix = make_index(m)
+        ix.encode_add(g["XP"])
+        got = ix.get_codes()
+        want_port = port.encode(m, g["XP"])
+        assert np.array_equal(got, want_port), f"{case}: device encode != oracle port"
+        # vs the reference: identical except float near-ties (Eigen reduction order)
+        _, margin = port.encode(m, g["XP"], with_margin=True)
+        diff = got != g["codes"]
+        assert diff.mean() < 1e-3
+        if diff.any():
+            assert (margin[diff] <= 1e-5 * max(1.0, float(margin.max()))).all()
+        ix.close()
+
+
+def test_synthetic_codes_match_host_generator():
+    from vaq_b200 import synth
+    rng = np.random.default_rng(5)
+    bits = [9, 8, 7, 6, 10, 3, 12, 5]
+    m = random_model(rng, len(bits), 2, bits)
+    for cdf in (None, synth.code_cdf(random_codes(rng, m, 5000), bits)):
+        ix = make_index(m)
+        ix.set_id_base(1_000_000_007)
+        ix.add_synthetic(5000, seed=99, cdf=cdf)
+        ix.add_synthetic(3001, seed=99, cdf=cdf)
+        got = ix.get_codes()
+        want = synth.synth_codes(bits, 8001, 1_000_000_007, 99, cdf)
+        assert np.array_equal(got, want)
+        ix.close()
+
+
+# ---- LUT ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", ["vaq_small_a", "vaq_small_b"])
+def test_lut_vs_reference(port, case):
+    g = load_golden(case)
+    m, _ = golden_model(g)
+    ix = make_index(m)
+    lut = ix.build_lut(g["Q"])
+    assert bitwise_equal(lut, port.create_lut(m, g["Q"])), "device LUT != oracle port (bitwise)"
+    for s in range(m.M):
+        a = lut[:, m.lut_off[s]:m.lut_off[s + 1]]
+        b = g["lut"][:, m.lut_off[s]:m.lut_off[s + 1]]
+        if m.K[s] >= 8:
+            assert bitwise_equal(a, b), f"subspace {s}: not bit-exact vs the reference's AVX2 path"
+        else:
+            np.testing.assert_allclose(a, b, rtol=RTOL, atol=0)
+    ix.close()
+
+
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 6, 8, 12, 15])
+def test_lut_all_sublens(port, L):
+    rng = np.random.default_rng(L)
+    bits = [10, 7, 4, 3, 2, 1]
+    m = random_model(rng, len(bits), L, bits)
+    q = rng.standard_normal((9, m.D)).astype(np.float32)
+    ix = make_index(m)
+    assert bitwise_equal(ix.build_lut(q), port.create_lut(m, q))
+    ix.close()
+
+
+# ---- search --------------------------------------------------------------------------------------
+
+def check_search(port, m, codes, Q, k, flags, ix=None, id_base=0):
+    from vaq_b200.index import PROJECTED
+    own = ix is None
+    if own:
+        ix = make_index(m, codes=codes)
+        if id_base:
+            ix.set_id_base(id_base)
+    lab, dis = ix.search(Q, k, flags | PROJECTED)
+    want_lab, want_dis = port.search_lex(m, codes, Q, k, id_base)
+    assert np.array_equal(lab, want_lab), "ids differ from the canonical (distance, id) top-k"
+    assert bitwise_equal(dis, want_dis), "distances are not bit-identical to the oracle's summation order"
+    if own:
+        ix.close()
+    return lab, dis
+
+
+@pytest.mark.parametrize("case", ["vaq_small_a", "vaq_small_b"])
+@pytest.mark.parametrize("mode", ["HEAP", "EA"])
+def test_search_vs_reference_fixture(port, case, mode):
+    from vaq_b200.index import EA, HEAP
+    g = load_golden(case)
+    m, _ = golden_model(g)
+    k = int(g["k"])
+    lab, dis = check_search(port, m, g["codes"], g["Q"], k, HEAP if mode == "HEAP" else EA)
+    key = "heap" if mode == "HEAP" else "ea"
+    assert_knn_equiv(lab, dis, g[f"lab_{key}"], g[f"dis_{key}"], what=f"{case}/{mode} vs reference")
+
+
+def test_search_raw_queries_device_projection(port):
+    from vaq_b200.index import EA
+    g = load_golden("vaq_small_a")
+    m, eig = golden_model(g)
+    ix = make_index(m, eig=eig, codes=g["codes"])
+    lab, dis = ix.search(g["Qraw"], int(g["k"]), EA)      # raw queries: (X * V) on the device
+    # projection order differs from Eigen's GEMM -> tolerance-only
+    np.testing.assert_allclose(dis, g["dis_ea"], rtol=2e-4)
+    assert (lab == g["lab_ea"]).mean() > 0.95
+    ix.close()
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 10), (31, 7), (32, 32), (33, 100), (1000, 100), (4097, 1), (20000, 10)])
+@pytest.mark.parametrize("mode", ["HEAP", "EA"])
+def test_search_ragged_sizes(port, n, k, mode):
+    from vaq_b200.index import EA, HEAP
+    rng = np.random.default_rng(n * 31 + k)
+    bits = [9, 8, 8, 7, 6, 6, 5, 4]
+    m = random_model(rng, 8, 4, bits)
+    codes = random_codes(rng, m, n)
+    Q = rng.standard_normal((5, m.D)).astype(np.float32) * 2
+    lab, dis = check_search(port, m, codes, Q, k, HEAP if mode == "HEAP" else EA)
+    if n < k:      # unfilled slots as utils/Heap.hpp:230-233,344-347 leaves them
+        assert (lab[:, n:] == -1).all()
+        assert (dis[:, n:] == np.finfo(np.float32).max).all()
+
+
+def test_search_duplicate_rows_tie_rule(port):
+    """Exact ties: every row repeated 4x -> canonical order keeps the lowest ids."""
+    from vaq_b200.index import EA
+    rng = np.random.default_rng(3)
+    m = random_model(rng, 8, 2, [6] * 8)
+    base = random_codes(rng, m, 500)
+    codes = np.concatenate([base] * 4)
+    Q = rng.standard_normal((8, m.D)).astype(np.float32)
+    check_search(port, m, codes, Q, 10, EA)
+
+
+def test_search_many_queries_and_id_base(port):
+    from vaq_b200.index import EA
+    rng = np.random.default_rng(8)
+    m = random_model(rng, 16, 2, [8] * 16)
+    codes = random_codes(rng, m, 30000)
+    Q = rng.standard_normal((700, m.D)).astype(np.float32)
+    check_search(port, m, codes, Q, 10, EA, id_base=123456789)
+
+
+def test_search_spill_path(port):
+    """sum K_s * 4 B beyond the shared-memory budget -> trailing tables served from L2 (GIST-512 shape)."""
+    from vaq_b200.index import EA, HEAP
+    rng = np.random.default_rng(21)
+    bits = [14, 14, 13, 13, 12, 12, 8, 8]        # 53 K + ... floats > 203 KB budget
+    m = random_model(rng, 8, 2, bits)
+    codes = random_codes(rng, m, 50000)
+    Q = rng.standard_normal((6, m.D)).astype(np.float32)
+    ix = make_index(m, codes=codes)
+    check_search(port, m, codes, Q, 10, EA, ix=ix)
+    cfg = ix.last_config()
+    assert cfg["spill_lut_floats"] > 0, cfg
+    check_search(port, m, codes, Q, 10, HEAP, ix=ix)
+    ix.close()
+
+
+def test_search_M_not_multiple_of_4(port):
+    """The reference misreads when mHighestSubs % 4 != 0; the device path is well defined:
+    same grouping with a short last group."""
+    from vaq_b200.index import EA
+    rng = np.random.default_rng(4)
+    m = random_model(rng, 6, 3, [7, 7, 6, 6, 5, 5])
+    codes = random_codes(rng, m, 3000)
+    Q = rng.standard_normal((4, m.D)).astype(np.float32)
+    ix = make_index(m, codes=codes)
+    lab, dis = ix.search(Q, 5, EA | 0x100)
+    lut = port.create_lut(m, Q)
+    for q in range(4):
+        d = np.zeros(3000, np.float32)
+        g1 = np.zeros(3000, np.float32)
+        for s in range(4):
+            g1 = g1 + lut[q, m.lut_off[s] + codes[:, s]]
+        g2 = np.zeros(3000, np.float32)
+        for s in range(4, 6):
+            g2 = g2 + lut[q, m.lut_off[s] + codes[:, s]]
+        d = (d + g1) + g2
+        order = np.lexsort((np.arange(3000), d))[:5]
+        assert np.array_equal(lab[q], order)
+        assert bitwise_equal(dis[q], d[order])
+    ix.close()
+
+
+def test_shard_invariance_and_key_merge(port):
+    """Rule 7: splitting the rows into G shards (id_base per shard) + key merge == one index."""
+    import torch
+    from vaq_b200.index import EA, PROJECTED
+    rng = np.random.default_rng(17)
+    m = random_model(rng, 8, 4, [9, 8, 8, 7, 7, 6, 6, 5])
+    n, k, nq = 40000, 10, 33
+    codes = random_codes(rng, m, n)
+    codes[n // 2:n // 2 + 2000] = codes[:2000]        # cross-shard exact ties
+    Q = rng.standard_normal((nq, m.D)).astype(np.float32)
+    want_lab, want_dis = port.search_lex(m, codes, Q, k)
+    dq = torch.from_numpy(Q).cuda()
+    for G in (1, 2, 4, 8):
+        bounds = [(n * r) // G for r in range(G + 1)]
+        keys = torch.empty((G, nq, k), dtype=torch.int64, device="cuda")
+        shards = []
+        for r in range(G):
+            ix = make_index(m, codes=codes[bounds[r]:bounds[r + 1]])
+            ix.set_id_base(bounds[r])
+            ix.search_keys_device(dq.data_ptr(), nq, k, EA | PROJECTED, keys[r].data_ptr(), torch.cuda.current_stream().cuda_stream)
+            shards.append(ix)
+        lab = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+        dis = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        shards[0].merge_keys_device(keys.data_ptr(), G, nq, k, 0, lab.data_ptr(), dis.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(lab.cpu().numpy(), want_lab), f"G={G}"
+        assert bitwise_equal(dis.cpu().numpy(), want_dis), f"G={G}"
+        for ix in shards:
+            ix.close()
+
+
+# ---- TI / visit, refine ---------------------------------------------------------------------------
+
+def test_ti_visit_vs_reference_fixture(port):
+    from vaq_b200.index import EA, PROJECTED, SQRT, TI
+    g = load_golden("vaq_small_a")
+    m, _ = golden_model(g)
+    ix = make_index(m, codes=g["ti_codes_grouped"])
+    ix.set_clusters(g["ti_clusters"], g["ti_start_idx"], g["ti_sizes"], g["ti_members"])
+    for visit in (1.0, 0.25):
+        ix.set_visit(visit)
+        lab, dis = ix.search(g["Q"], int(g["k"]), TI | EA | PROJECTED | SQRT)
+        tag = f"v{int(visit * 100)}"
+        assert_knn_equiv(lab, dis, g[f"ti_lab_{tag}"], g[f"ti_dis_{tag}"], what=f"TI visit={visit} vs reference")
+    ix.close()
+
+
+def test_refine_vs_reference_fixture(port):
+    for case in ("vaq_small_a", "vaq_small_b"):
+        g = load_golden(case)
+        m, _ = golden_model(g)
+        X, Q = g["X"], g["Qraw"]
+        ix = make_index(m)
+        ix.set_raw_vectors(X)
+        lab, dis = ix.refine(Q, g["lab_heap"], int(g["kr"]))
+        assert_knn_equiv(lab, dis, g["refine_lab"], g["refine_dis"], rtol=1e-5, what=f"{case}/refine")
+        ix.close()
+
+
+# ---- errors ----------------------------------------------------------------------------------------
+
+def test_error_paths():
+    from vaq_b200 import _lib
+    from vaq_b200.index import EA, TI, VAQIndex
+    rng = np.random.default_rng(0)
+    m = random_model(rng, 4, 2, [4, 4, 4, 4])
+    ix = make_index(m, codes=random_codes(rng, m, 100))
+    q = np.zeros((1, m.D), np.float32)
+    with pytest.raises(_lib.VaqGpuError) as e:
+        ix.search(q, 5, EA)                      # raw queries without eigenvectors
+    assert e.value.code == _lib.VAQGPU_ESTATE
+    with pytest.raises(_lib.VaqGpuError) as e:
+        ix.search(q, 5, TI | 0x100)              # TI without clusters
+    assert e.value.code == _lib.VAQGPU_ESTATE
+    with pytest.raises(_lib.VaqGpuError) as e:
+        ix.search(q, 0, EA | 0x100)
+    assert e.value.code == _lib.VAQGPU_EINVAL
+    with pytest.raises(_lib.VaqGpuError):
+        ix.get_codes(90, 20)
+    with pytest.raises(_lib.VaqGpuError):
+        VAQIndex(2, [16, 4], [np.zeros((1 << 16, 2), np.float32), np.zeros((16, 2), np.float32)])
+    lab, dis = ix.search(np.zeros((0, m.D), np.float32), 5, EA | 0x100)   # empty batch is a no-op
+    assert lab.shape == (0, 5)
+    ix.close()

@@ -1,0 +1,72 @@
+"""Builds vaq_b200/libvaqgpu.so (sm_100a only) from vaq_b200/csrc/*.cu with nvcc.
+
+In-tree on purpose: the .so travels with the repo snapshot to the GPU box and is the
+file the driver looks for when it checks that native code was loaded.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+OBJ = PKG / "csrc" / "_obj"
+LIB = PKG / "libvaqgpu.so"
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and Path(c).exists():
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "vaqgpu.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    OBJ.mkdir(exist_ok=True)
+    flags = list(NVCC_FLAGS)
+
+    def compile_one(src: Path):
+        obj = OBJ / (src.stem + ".o")
+        r = subprocess.run([nvcc, *flags, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name}:\n{r.stdout}\n{r.stderr}")
+        (OBJ / (src.stem + ".ptxas.txt")).write_text(r.stderr)
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    r = subprocess.run([nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,861 @@
+// C-ABI implementation (include/vaqgpu.h): index state in HBM, scan planning, launch
+// sequencing.  No CPU fallback: every entry point fails with VAQGPU_ECUDA when there is no
+// usable sm_100 device.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/vaqgpu.h"
+#include "common.cuh"
+
+using namespace vaqgpu;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? VAQGPU_ENOMEM : VAQGPU_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                  cudaGetErrorString(e_));                                                         \
+  } while (0)
+
+constexpr int kScanThreads = 256;
+constexpr size_t kSmemCap = 227 * 1024;           // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t kLutWorkspaceBytes = 1ull << 30; // LUT workspace cap -> queries per launch
+constexpr int64_t kStageRows = 1 << 21;           // rows per upload / generate chunk
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(VAQGPU_ECUDA, "no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(VAQGPU_EINVAL, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, device);
+  if (e != cudaSuccess) return fail(VAQGPU_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (p.major != 10) return fail(VAQGPU_ECUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, p.major, p.minor);
+  return VAQGPU_OK;
+}
+
+}  // namespace
+
+struct vaqgpu_index {
+  int device = 0;
+  int num_sms = 148;
+  int D = 0, M = 0, L = 0;
+  std::vector<int32_t> bits;
+  int32_t total_entries = 0;
+  int64_t id_base = 0;
+  float visit = 1.f;
+
+  ScanLayout lay{};
+  LutPlan plan{};
+  int32_t smem_lut_floats = 0, spill_floats = 0;
+
+  float *d_centroids = nullptr;
+  float *d_eig = nullptr;
+  int32_t *d_bits = nullptr, *d_ent_off = nullptr;
+
+  uint4 *d_codes = nullptr;
+  int64_t n_rows = 0, cap_rows = 0;
+
+  // TI / visit
+  int32_t C = 0, segdims = 0;
+  float *d_clusters = nullptr;
+  int64_t *d_cl_start = nullptr, *d_cl_size = nullptr;
+  int32_t *d_id_map = nullptr;
+
+  // refine
+  float *d_raw = nullptr;
+  int64_t raw_n = 0;
+  int32_t raw_D = 0;
+
+  cudaStream_t stream = nullptr;   // used by the host-buffer entry points
+  cudaEvent_t ev[5] = {};
+  bool timed = false;
+  int32_t cfg[8] = {};
+
+  DevBuf w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
+};
+
+struct hamgpu_index {
+  int device = 0;
+  int num_sms = 148;
+  int nbits = 0, w64 = 0, W = 0;
+  int64_t id_base = 0;
+  uint4 *d_codes = nullptr;
+  int64_t n_rows = 0, cap_rows = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {};
+  bool timed = false;
+  int32_t cfg[8] = {};
+  DevBuf w_q, w_qpad, w_keys, w_scratch, w_stage, w_idx, w_dist;
+};
+
+namespace {
+
+// Grow a tiled code matrix to hold at least `rows` rows (whole 32-row tiles, zero-filled so the
+// padding rows of the last tile decode to valid table indices).
+cudaError_t grow_codes(uint4 **codes, int64_t *cap_rows, int64_t n_rows, int W, int64_t rows, cudaStream_t st) {
+  if (rows <= *cap_rows) return cudaSuccess;
+  int64_t want = std::max<int64_t>(rows, *cap_rows + *cap_rows / 2);
+  want = (want + kTileRows - 1) / kTileRows * kTileRows;
+  uint4 *nw = nullptr;
+  const size_t bytes = (size_t)want * W * sizeof(uint4);
+  cudaError_t e = cudaMalloc(&nw, bytes);
+  if (e != cudaSuccess && want > rows) {          // retry without head-room
+    cudaGetLastError();
+    want = (rows + kTileRows - 1) / kTileRows * kTileRows;
+    e = cudaMalloc(&nw, (size_t)want * W * sizeof(uint4));
+  }
+  if (e != cudaSuccess) return e;
+  const int64_t used_rows = (n_rows + kTileRows - 1) / kTileRows * kTileRows;
+  const size_t used = (size_t)used_rows * W * sizeof(uint4);
+  if (*codes && used) {
+    e = cudaMemcpyAsync(nw, *codes, used, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { cudaFree(nw); return e; }
+  }
+  e = cudaMemsetAsync(reinterpret_cast<unsigned char *>(nw) + used, 0, (size_t)want * W * sizeof(uint4) - used, st);
+  if (e != cudaSuccess) { cudaFree(nw); return e; }
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaFree(nw); return e; }
+  if (*codes) cudaFree(*codes);
+  *codes = nw;
+  *cap_rows = want;
+  return cudaSuccess;
+}
+
+// Field placement inside the packed row + LUT placement (shared-memory resident vs spilled).
+int plan_model(vaqgpu_index *h) {
+  const int M = h->M;
+  ScanLayout &lay = h->lay;
+  LutPlan &plan = h->plan;
+  memset(&lay, 0, sizeof(lay));
+  memset(&plan, 0, sizeof(plan));
+  int64_t bitoff = 0;
+  int32_t ent = 0, coff = 0;
+  std::vector<int> word_of(M);
+  for (int s = 0; s < M; s++) {
+    const int b = h->bits[s];
+    word_of[s] = (int)(bitoff >> 5);
+    lay.fmeta[s] = (uint32_t)(bitoff & 31) | ((uint32_t)((1u << b) - 1u) << 16);
+    plan.ent_off[s] = ent;
+    plan.cent_off[s] = coff;
+    ent += 1 << b;
+    coff += (1 << b) * h->L;
+    bitoff += b;
+  }
+  plan.ent_off[M] = ent;
+  plan.M = M; plan.L = h->L; plan.total_entries = ent;
+  h->total_entries = ent;
+  const int W = (int)((bitoff + 127) / 128);
+  if (W < 1 || W > 8) return fail(VAQGPU_EINVAL, "sum(bits)=%lld needs %d uint4 words per row; supported 1..8", (long long)bitoff, W);
+  lay.M = M; lay.W = W;
+  int f = 0;
+  for (int w = 0; w <= 4 * W; w++) {
+    while (f < M && word_of[f] < w) f++;
+    lay.fbeg[w] = (uint16_t)f;
+  }
+  lay.fbeg[4 * W] = (uint16_t)M;
+
+  // LUT residency: tables are taken in scan order (variance-descending — with early abandon the
+  // leading tables are the ones every row touches) while they fit the shared-memory budget; the
+  // rest stay in global memory and are served by L1/L2.
+  const size_t list_reserve = 24 * 1024;    // top-k lists, merge buffer, barrier
+  const size_t budget_floats = (kSmemCap - list_reserve) / 4;
+  // if everything fits in half the SM, keep it all (two CTAs per SM); otherwise fill one CTA's budget
+  size_t resident = 0;
+  std::vector<char> res(M, 0);
+  for (int s = 0; s < M; s++) {
+    const size_t K = (size_t)1 << h->bits[s];
+    if (resident + K <= budget_floats) { res[s] = 1; resident += K; }
+  }
+  int32_t pos = 0;
+  for (int s = 0; s < M; s++)
+    if (res[s]) { plan.pos[s] = pos; lay.foff[s] = (uint32_t)pos; pos += 1 << h->bits[s]; }
+  const int32_t res_floats = (pos + 3) & ~3;
+  int32_t sp = 0;
+  for (int s = 0; s < M; s++)
+    if (!res[s]) {
+      plan.pos[s] = res_floats + sp; lay.foff[s] = (uint32_t)sp; lay.fmeta[s] |= kFieldSpill; sp += 1 << h->bits[s];
+    }
+  h->smem_lut_floats = res_floats;
+  h->spill_floats = sp;
+  plan.row_stride = (res_floats + sp + 3) & ~3;
+  return VAQGPU_OK;
+}
+
+size_t scan_smem_bytes(const vaqgpu_index *h, int k, int threads) {
+  const int nwarps = threads / 32;
+  size_t b = (((size_t)h->smem_lut_floats * 4 + 15) & ~(size_t)15);
+  b += ((size_t)nwarps * k + k + 2) * sizeof(uint64_t);
+  return b;
+}
+
+int ensure_stream(cudaStream_t *st, cudaEvent_t *ev, int nev) {
+  if (!*st) CU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+  for (int i = 0; i < nev; i++)
+    if (!ev[i]) CU(cudaEventCreate(&ev[i]));
+  return VAQGPU_OK;
+}
+
+__global__ void ham_pad_queries_kernel(const uint64_t *__restrict__ q, int nq, int w64, int W, uint4 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq * W) return;
+  const int r = i / W, j = i - r * W;
+  const uint64_t a = (2 * j < w64) ? q[(size_t)r * w64 + 2 * j] : 0ull;
+  const uint64_t b = (2 * j + 1 < w64) ? q[(size_t)r * w64 + 2 * j + 1] : 0ull;
+  out[i] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+}
+
+// The whole device-side search; exactly one of (d_labels,d_dists) / d_keys is the output.
+int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, uint32_t flags, int32_t *d_labels,
+                       float *d_dists, uint64_t *d_keys, cudaStream_t st, bool record) {
+  if (nq < 0 || k <= 0) return fail(VAQGPU_EINVAL, "nq=%d k=%d", nq, k);
+  if (k > 2048) return fail(VAQGPU_EINVAL, "k=%d > 2048 unsupported", k);
+  if (nq == 0) return VAQGPU_OK;
+  const bool projected = flags & VAQGPU_PROJECTED;
+  if (!projected && !h->d_eig) return fail(VAQGPU_ESTATE, "raw queries need eig_real in the model (or pass VAQGPU_PROJECTED)");
+  const bool ti = (flags & VAQGPU_TI) != 0;
+  if (ti && !h->d_clusters) return fail(VAQGPU_ESTATE, "VAQGPU_TI needs vaqgpu_set_clusters");
+  // the reference dispatches TI -> EA -> HEAP (VAQ.cpp:799-840); HEAP alone is the exhaustive scan
+  const bool ea = (flags & VAQGPU_EA) != 0 || ti || !(flags & VAQGPU_HEAP);
+  const int threads = kScanThreads;
+  const size_t smem = scan_smem_bytes(h, k, threads);
+  if (smem > kSmemCap) return fail(VAQGPU_EINVAL, "k=%d needs %zu B shared memory (> %zu)", k, smem, kSmemCap);
+  int launches = 0;
+
+  if (record) CU(cudaEventRecord(h->ev[0], st));
+  const float *d_qproj = d_queries;
+  if (!projected) {
+    CU(h->w_qproj.ensure((size_t)nq * h->D * sizeof(float)));
+    CU(launch_project(d_queries, nq, h->D, h->d_eig, (float *)h->w_qproj.p, st));
+    d_qproj = (const float *)h->w_qproj.p;
+    launches++;
+  }
+  if (record) CU(cudaEventRecord(h->ev[1], st));
+
+  int ctas_per_sm = 1;
+  CU(adc_scan_occupancy(h->lay.W, threads, smem, &ctas_per_sm));
+  if (ctas_per_sm < 1) return fail(VAQGPU_ECUDA, "ADC scan kernel does not fit an SM with %zu B shared memory", smem);
+  const int64_t n_tiles = (h->n_rows + kTileRows - 1) / kTileRows;
+  const int nwarps = threads / 32;
+  const int qb_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)nq, kLutWorkspaceBytes / ((size_t)h->plan.row_stride * 4)));
+  // CTAs per query: fill ~2 waves of the machine when there are few queries, but leave each
+  // warp at least 8 tiles so the per-CTA LUT staging stays amortised.
+  const int64_t target = (int64_t)h->num_sms * ctas_per_sm * 2;
+  int splits = (int)std::max<int64_t>(1, (target + std::min(nq, qb_max) - 1) / std::min(nq, qb_max));
+  const int64_t max_splits = std::max<int64_t>(1, n_tiles / (nwarps * 8));
+  splits = (int)std::min<int64_t>(splits, max_splits);
+  if (ti) splits = std::min(splits, 4);
+
+  CU(h->w_lut.ensure((size_t)qb_max * h->plan.row_stride * sizeof(float)));
+  CU(h->w_keys.ensure((size_t)qb_max * splits * k * sizeof(uint64_t)));
+  if (splits > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((splits + 15) / 16) * k * sizeof(uint64_t)));
+  if (ti) {
+    CU(h->w_ranges.ensure((size_t)qb_max * h->C * sizeof(int2)));
+    CU(h->w_nranges.ensure((size_t)qb_max * sizeof(int32_t)));
+  }
+
+  for (int q0 = 0; q0 < nq; q0 += qb_max) {
+    const int qb = std::min(qb_max, nq - q0);
+    const float *qp = d_qproj + (size_t)q0 * h->D;
+    if (ti) {
+      CU(launch_rank_clusters(qp, qb, h->D, h->d_clusters, h->C, h->segdims, h->d_cl_start, h->d_cl_size, h->visit, k,
+                              (int2 *)h->w_ranges.p, (int32_t *)h->w_nranges.p, st));
+      launches++;
+    }
+    CU(launch_lut_build(qp, qb, h->D, h->d_centroids, h->plan, (float *)h->w_lut.p, st));
+    launches++;
+    if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
+    AdcScanArgs a{};
+    a.codes = h->d_codes; a.n_rows = h->n_rows;
+    a.lut = (const float *)h->w_lut.p; a.lut_stride = h->plan.row_stride;
+    a.smem_lut_floats = h->smem_lut_floats;
+    a.nq = qb; a.k = k; a.splits = splits;
+    a.early_abandon = ea ? 1 : 0;
+    a.use_tma = 1;
+    a.out_keys = (uint64_t *)h->w_keys.p;
+    if (ti) { a.ranges = (const int2 *)h->w_ranges.p; a.n_ranges = (const int32_t *)h->w_nranges.p; a.max_ranges = h->C; }
+    a.lay = h->lay;
+    CU(launch_adc_scan(a, threads, smem, st));
+    launches++;
+    if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
+    const bool want_sqrt = (flags & VAQGPU_SQRT) != 0;
+    CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)splits * k, splits, qb, k, want_sqrt ? 1 : 0, 0,
+                         d_labels ? d_labels + (size_t)q0 * k : nullptr, d_dists ? (void *)(d_dists + (size_t)q0 * k) : nullptr,
+                         d_keys ? d_keys + (size_t)q0 * k : nullptr, ti ? h->d_id_map : nullptr, h->id_base,
+                         (uint64_t *)h->w_scratch.p, st));
+    launches += splits > 16 ? 2 : 1;
+  }
+  if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
+  h->cfg[0] = threads; h->cfg[1] = splits; h->cfg[2] = h->smem_lut_floats; h->cfg[3] = h->spill_floats;
+  h->cfg[4] = (int32_t)smem; h->cfg[5] = h->lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
+  return VAQGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *vaqgpu_last_error(void) { return g_err; }
+
+int vaqgpu_device_count(int *count) {
+  if (!count) return fail(VAQGPU_EINVAL, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return fail(VAQGPU_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  *count = n;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_create(const vaqgpu_model_desc *m, int device, vaqgpu_t **out) {
+  if (!m || !out) return fail(VAQGPU_EINVAL, "model/out is NULL");
+  *out = nullptr;
+  if (m->M < 1 || m->M > kMaxSubspaces) return fail(VAQGPU_EINVAL, "M=%d out of range [1,%d]", m->M, kMaxSubspaces);
+  if (m->L < 1 || m->L > 256) return fail(VAQGPU_EINVAL, "L=%d out of range", m->L);
+  if (m->D != m->M * m->L) return fail(VAQGPU_EINVAL, "D=%d != M*L=%d", m->D, m->M * m->L);
+  if (!m->bits || !m->centroids) return fail(VAQGPU_EINVAL, "bits/centroids is NULL");
+  int64_t sum = 0;
+  for (int s = 0; s < m->M; s++) {
+    if (m->bits[s] < 1 || m->bits[s] > 15) return fail(VAQGPU_EINVAL, "bits[%d]=%d out of range [1,15]", s, m->bits[s]);
+    sum += m->bits[s];
+  }
+  if (sum > 1024) return fail(VAQGPU_EINVAL, "sum(bits)=%lld > 1024", (long long)sum);
+  int rc = check_device(device);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  vaqgpu_index *h = new (std::nothrow) vaqgpu_index();
+  if (!h) return fail(VAQGPU_ENOMEM, "host allocation failed");
+  h->device = device;
+  h->D = m->D; h->M = m->M; h->L = m->L;
+  h->bits.assign(m->bits, m->bits + m->M);
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+  rc = plan_model(h);
+  if (rc) { delete h; return rc; }
+#define CUX(call)                                                                                        \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      vaqgpu_destroy(h);                                                                                 \
+      return fail(VAQGPU_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));                                \
+    }                                                                                                    \
+  } while (0)
+  size_t cent_floats = 0;
+  for (int s = 0; s < m->M; s++) cent_floats += ((size_t)1 << m->bits[s]) * m->L;
+  CUX(cudaMalloc(&h->d_centroids, cent_floats * sizeof(float)));
+  CUX(cudaMemcpy(h->d_centroids, m->centroids, cent_floats * sizeof(float), cudaMemcpyHostToDevice));
+  if (m->eig_real) {
+    CUX(cudaMalloc(&h->d_eig, (size_t)m->D * m->D * sizeof(float)));
+    CUX(cudaMemcpy(h->d_eig, m->eig_real, (size_t)m->D * m->D * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  CUX(cudaMalloc(&h->d_bits, m->M * sizeof(int32_t)));
+  CUX(cudaMemcpy(h->d_bits, m->bits, m->M * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUX(cudaMalloc(&h->d_ent_off, (m->M + 1) * sizeof(int32_t)));
+  CUX(cudaMemcpy(h->d_ent_off, h->plan.ent_off, (m->M + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUX(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto &e : h->ev) CUX(cudaEventCreate(&e));
+#undef CUX
+  *out = h;
+  return VAQGPU_OK;
+}
+
+void vaqgpu_destroy(vaqgpu_t *h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_centroids); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
+  cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size);
+  cudaFree(h->d_id_map); cudaFree(h->d_raw);
+  for (DevBuf *b : {&h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
+                    &h->w_labels, &h->w_dists, &h->w_outkeys, &h->w_cdf, &h->w_x})
+    b->release();
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int vaqgpu_set_id_base(vaqgpu_t *h, int64_t id_base) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  h->id_base = id_base;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_reserve(vaqgpu_t *h, int64_t n_total) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  DeviceGuard g(h->device);
+  if (n_total > h->cap_rows) {
+    // exact reservation (no head-room) by temporarily pretending the capacity is full
+    int64_t cap = h->cap_rows;
+    int64_t want = (n_total + kTileRows - 1) / kTileRows * kTileRows;
+    uint4 *nw = nullptr;
+    CU(cudaMalloc(&nw, (size_t)want * h->lay.W * sizeof(uint4)));
+    const int64_t used_rows = (h->n_rows + kTileRows - 1) / kTileRows * kTileRows;
+    const size_t used = (size_t)used_rows * h->lay.W * sizeof(uint4);
+    if (h->d_codes && used) CU(cudaMemcpyAsync(nw, h->d_codes, used, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemsetAsync(reinterpret_cast<unsigned char *>(nw) + used, 0, (size_t)want * h->lay.W * sizeof(uint4) - used, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->d_codes) cudaFree(h->d_codes);
+    h->d_codes = nw;
+    h->cap_rows = want;
+    (void)cap;
+  }
+  return VAQGPU_OK;
+}
+
+int vaqgpu_add_codes_u16(vaqgpu_t *h, const uint16_t *codes, int64_t n) {
+  if (!h || (!codes && n > 0)) return fail(VAQGPU_EINVAL, "handle/codes is NULL");
+  if (n < 0) return fail(VAQGPU_EINVAL, "n=%lld", (long long)n);
+  if (n == 0) return VAQGPU_OK;
+  if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index (labels are int32, utils/Types.hpp:100)");
+  DeviceGuard g(h->device);
+  CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
+  const int64_t chunk = std::min<int64_t>(n, kStageRows);
+  CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
+  for (int64_t r = 0; r < n; r += chunk) {
+    const int64_t c = std::min(chunk, n - r);
+    CU(cudaMemcpyAsync(h->w_stage.p, codes + (size_t)r * h->M, (size_t)c * h->M * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_pack_codes((const uint16_t *)h->w_stage.p, c, h->n_rows + r, h->lay, h->d_codes, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  h->n_rows += n;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_encode_add(vaqgpu_t *h, const float *x_proj, int64_t n) {
+  if (!h || (!x_proj && n > 0)) return fail(VAQGPU_EINVAL, "handle/x_proj is NULL");
+  if (n < 0) return fail(VAQGPU_EINVAL, "n=%lld", (long long)n);
+  if (n == 0) return VAQGPU_OK;
+  if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index");
+  DeviceGuard g(h->device);
+  CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
+  const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t)(256ull << 20) / (h->D * 4)));
+  CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
+  CU(h->w_x.ensure((size_t)chunk * h->D * sizeof(float)));
+  for (int64_t r = 0; r < n; r += chunk) {
+    const int64_t c = std::min(chunk, n - r);
+    CU(cudaMemcpyAsync(h->w_x.p, x_proj + (size_t)r * h->D, (size_t)c * h->D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_encode((const float *)h->w_x.p, c, h->d_centroids, h->plan, (uint16_t *)h->w_stage.p, h->stream));
+    CU(launch_pack_codes((const uint16_t *)h->w_stage.p, c, h->n_rows + r, h->lay, h->d_codes, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  h->n_rows += n;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_add_codes_synthetic(vaqgpu_t *h, int64_t n, uint64_t seed, const float *cdf) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  if (n < 0) return fail(VAQGPU_EINVAL, "n=%lld", (long long)n);
+  if (n == 0) return VAQGPU_OK;
+  if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index");
+  DeviceGuard g(h->device);
+  CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
+  const float *d_cdf = nullptr;
+  if (cdf) {
+    CU(h->w_cdf.ensure((size_t)h->total_entries * sizeof(float)));
+    CU(cudaMemcpyAsync(h->w_cdf.p, cdf, (size_t)h->total_entries * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    d_cdf = (const float *)h->w_cdf.p;
+  }
+  const int64_t chunk = std::min<int64_t>(n, kStageRows);
+  CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
+  for (int64_t r = 0; r < n; r += chunk) {
+    const int64_t c = std::min(chunk, n - r);
+    CU(launch_synth_codes((uint16_t *)h->w_stage.p, c, h->id_base + h->n_rows + r, h->M, h->d_bits, d_cdf, h->d_ent_off, seed, h->stream));
+    CU(launch_pack_codes((const uint16_t *)h->w_stage.p, c, h->n_rows + r, h->lay, h->d_codes, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  h->n_rows += n;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_num_rows(const vaqgpu_t *h, int64_t *n) {
+  if (!h || !n) return fail(VAQGPU_EINVAL, "handle/n is NULL");
+  *n = h->n_rows;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_row_bytes(const vaqgpu_t *h, int32_t *bytes) {
+  if (!h || !bytes) return fail(VAQGPU_EINVAL, "handle/bytes is NULL");
+  *bytes = h->lay.W * 16;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_get_codes_u16(vaqgpu_t *h, int64_t row0, int64_t n, uint16_t *out) {
+  if (!h || (!out && n > 0)) return fail(VAQGPU_EINVAL, "handle/out is NULL");
+  if (row0 < 0 || n < 0 || row0 + n > h->n_rows) return fail(VAQGPU_EINVAL, "rows [%lld,%lld) outside [0,%lld)", (long long)row0, (long long)(row0 + n), (long long)h->n_rows);
+  if (n == 0) return VAQGPU_OK;
+  DeviceGuard g(h->device);
+  const int64_t chunk = std::min<int64_t>(n, kStageRows);
+  CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
+  for (int64_t r = 0; r < n; r += chunk) {
+    const int64_t c = std::min(chunk, n - r);
+    CU(launch_unpack_codes(h->d_codes, row0 + r, c, h->lay, (uint16_t *)h->w_stage.p, h->stream));
+    CU(cudaMemcpyAsync(out + (size_t)r * h->M, h->w_stage.p, (size_t)c * h->M * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return VAQGPU_OK;
+}
+
+int vaqgpu_build_lut(vaqgpu_t *h, const float *q_proj, int32_t nq, float *lut_out) {
+  if (!h || !q_proj || !lut_out) return fail(VAQGPU_EINVAL, "handle/q_proj/lut_out is NULL");
+  if (nq <= 0) return nq == 0 ? VAQGPU_OK : fail(VAQGPU_EINVAL, "nq=%d", nq);
+  DeviceGuard g(h->device);
+  // compact plan: table s at ent_off[s]
+  LutPlan p = h->plan;
+  for (int s = 0; s < h->M; s++) p.pos[s] = p.ent_off[s];
+  p.row_stride = p.total_entries;
+  CU(h->w_q.ensure((size_t)nq * h->D * sizeof(float)));
+  CU(h->w_lut.ensure((size_t)nq * p.row_stride * sizeof(float)));
+  CU(cudaMemcpyAsync(h->w_q.p, q_proj, (size_t)nq * h->D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(launch_lut_build((const float *)h->w_q.p, nq, h->D, h->d_centroids, p, (float *)h->w_lut.p, h->stream));
+  CU(cudaMemcpyAsync(lut_out, h->w_lut.p, (size_t)nq * p.row_stride * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VAQGPU_OK;
+}
+
+int vaqgpu_search_device(vaqgpu_t *h, const float *d_queries, int32_t nq, int32_t k, uint32_t flags, int32_t *d_labels,
+                         float *d_dists, void *stream) {
+  if (!h || (nq > 0 && (!d_queries || !d_labels || !d_dists))) return fail(VAQGPU_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  return search_device_impl(h, d_queries, nq, k, flags, d_labels, d_dists, nullptr, (cudaStream_t)stream, true);
+}
+
+int vaqgpu_search_keys_device(vaqgpu_t *h, const float *d_queries, int32_t nq, int32_t k, uint32_t flags, uint64_t *d_keys,
+                              void *stream) {
+  if (!h || (nq > 0 && (!d_queries || !d_keys))) return fail(VAQGPU_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  return search_device_impl(h, d_queries, nq, k, flags & ~VAQGPU_SQRT, nullptr, nullptr, d_keys, (cudaStream_t)stream, true);
+}
+
+int vaqgpu_merge_keys_device(const uint64_t *d_keys_in, int32_t G, int32_t nq, int32_t k, uint32_t flags, int32_t *d_labels,
+                             float *d_dists, void *stream) {
+  if (!d_keys_in || !d_labels || !d_dists) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (G < 1 || G > 16 || nq < 0 || k <= 0) return fail(VAQGPU_EINVAL, "G=%d (1..16) nq=%d k=%d", G, nq, k);
+  CU(launch_merge_keys(d_keys_in, (int64_t)nq * k, k, G, nq, k, (flags & VAQGPU_SQRT) ? 1 : 0, 0, d_labels, d_dists, nullptr,
+                       nullptr, 0, nullptr, (cudaStream_t)stream));
+  return VAQGPU_OK;
+}
+
+int vaqgpu_search(vaqgpu_t *h, const float *queries, int32_t nq, int32_t k, uint32_t flags, int32_t *labels, float *dists) {
+  if (!h || (nq > 0 && (!queries || !labels || !dists))) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (nq < 0 || k <= 0) return fail(VAQGPU_EINVAL, "nq=%d k=%d", nq, k);
+  if (nq == 0) return VAQGPU_OK;
+  DeviceGuard g(h->device);
+  CU(h->w_q.ensure((size_t)nq * h->D * sizeof(float)));
+  CU(h->w_labels.ensure((size_t)nq * k * sizeof(int32_t)));
+  CU(h->w_dists.ensure((size_t)nq * k * sizeof(float)));
+  CU(cudaMemcpyAsync(h->w_q.p, queries, (size_t)nq * h->D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  int rc = search_device_impl(h, (const float *)h->w_q.p, nq, k, flags, (int32_t *)h->w_labels.p, (float *)h->w_dists.p, nullptr,
+                              h->stream, true);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(labels, h->w_labels.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(dists, h->w_dists.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VAQGPU_OK;
+}
+
+int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t segdims, const int64_t *start,
+                        const int64_t *size, const int32_t *id_map) {
+  if (!h || !clusters || !start || !size) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (C < 1 || segdims < 1 || segdims > h->D) return fail(VAQGPU_EINVAL, "C=%d segdims=%d", C, segdims);
+  for (int c = 0; c < C; c++)
+    if (start[c] < 0 || size[c] < 0 || start[c] + size[c] > h->n_rows)
+      return fail(VAQGPU_EINVAL, "cluster %d range [%lld,+%lld) outside the index (%lld rows)", c, (long long)start[c], (long long)size[c], (long long)h->n_rows);
+  DeviceGuard g(h->device);
+  cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_id_map);
+  h->d_clusters = nullptr; h->d_cl_start = h->d_cl_size = nullptr; h->d_id_map = nullptr;
+  CU(cudaMalloc(&h->d_clusters, (size_t)C * segdims * sizeof(float)));
+  CU(cudaMemcpy(h->d_clusters, clusters, (size_t)C * segdims * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&h->d_cl_start, (size_t)C * sizeof(int64_t)));
+  CU(cudaMemcpy(h->d_cl_start, start, (size_t)C * sizeof(int64_t), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&h->d_cl_size, (size_t)C * sizeof(int64_t)));
+  CU(cudaMemcpy(h->d_cl_size, size, (size_t)C * sizeof(int64_t), cudaMemcpyHostToDevice));
+  if (id_map) {
+    CU(cudaMalloc(&h->d_id_map, (size_t)h->n_rows * sizeof(int32_t)));
+    CU(cudaMemcpy(h->d_id_map, id_map, (size_t)h->n_rows * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  h->C = C; h->segdims = segdims;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_set_visit(vaqgpu_t *h, float visit) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  if (!(visit > 0.f)) return fail(VAQGPU_EINVAL, "visit=%f must be > 0", visit);
+  h->visit = visit;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_set_raw_vectors(vaqgpu_t *h, const float *xtrain, int64_t n, int32_t D0) {
+  if (!h || !xtrain) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (n <= 0 || D0 <= 0) return fail(VAQGPU_EINVAL, "n=%lld D0=%d", (long long)n, D0);
+  DeviceGuard g(h->device);
+  cudaFree(h->d_raw); h->d_raw = nullptr;
+  CU(cudaMalloc(&h->d_raw, (size_t)n * D0 * sizeof(float)));
+  CU(cudaMemcpy(h->d_raw, xtrain, (size_t)n * D0 * sizeof(float), cudaMemcpyHostToDevice));
+  h->raw_n = n; h->raw_D = D0;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_refine(vaqgpu_t *h, const float *queries, int32_t nq, const int32_t *in_labels, int32_t refine_num, int32_t k,
+                  int32_t *labels, float *dists) {
+  if (!h || !queries || !in_labels || !labels || !dists) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (!h->d_raw) return fail(VAQGPU_ESTATE, "vaqgpu_refine needs vaqgpu_set_raw_vectors");
+  if (nq <= 0 || refine_num <= 0 || k <= 0 || k > refine_num) return fail(VAQGPU_EINVAL, "nq=%d refine_num=%d k=%d", nq, refine_num, k);
+  if ((size_t)refine_num * 8 > kSmemCap) return fail(VAQGPU_EINVAL, "refine_num=%d too large", refine_num);
+  DeviceGuard g(h->device);
+  const int D0 = h->raw_D;
+  CU(h->w_q.ensure((size_t)nq * D0 * sizeof(float)));
+  CU(h->w_stage.ensure((size_t)nq * refine_num * sizeof(int32_t)));
+  CU(h->w_labels.ensure((size_t)nq * k * sizeof(int32_t)));
+  CU(h->w_dists.ensure((size_t)nq * k * sizeof(float)));
+  CU(cudaMemcpyAsync(h->w_q.p, queries, (size_t)nq * D0 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->w_stage.p, in_labels, (size_t)nq * refine_num * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(launch_refine(h->d_raw, h->raw_n, D0, (const float *)h->w_q.p, nq, (const int32_t *)h->w_stage.p, refine_num, k,
+                   (int32_t *)h->w_labels.p, (float *)h->w_dists.p, h->stream));
+  CU(cudaMemcpyAsync(labels, h->w_labels.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(dists, h->w_dists.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VAQGPU_OK;
+}
+
+int vaqgpu_last_timings(const vaqgpu_t *h, float ms[4]) {
+  if (!h || !ms) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (!h->timed) return fail(VAQGPU_ESTATE, "no search has run on this handle");
+  DeviceGuard g(h->device);
+  CU(cudaEventSynchronize(h->ev[4]));
+  for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+  return VAQGPU_OK;
+}
+
+int vaqgpu_last_config(const vaqgpu_t *h, int32_t cfg[8]) {
+  if (!h || !cfg) return fail(VAQGPU_EINVAL, "NULL argument");
+  memcpy(cfg, h->cfg, sizeof(h->cfg));
+  return VAQGPU_OK;
+}
+
+/* ---------------------------------------------------------------- Hamming ---- */
+
+int hamgpu_create(int32_t nbits, int device, hamgpu_t **out) {
+  if (!out) return fail(VAQGPU_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (nbits < 1 || nbits > 1024) return fail(VAQGPU_EINVAL, "nbits=%d out of range [1,1024]", nbits);
+  const int W = (nbits + 127) / 128;
+  if (W == 5 || W == 7) return fail(VAQGPU_EINVAL, "nbits=%d (%d x 128-bit words) unsupported: use 1,2,3,4,6 or 8 words", nbits, W);
+  int rc = check_device(device);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  hamgpu_index *h = new (std::nothrow) hamgpu_index();
+  if (!h) return fail(VAQGPU_ENOMEM, "host allocation failed");
+  h->device = device; h->nbits = nbits; h->w64 = (nbits + 63) / 64; h->W = W;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+  rc = ensure_stream(&h->stream, h->ev, 3);
+  if (rc) { hamgpu_destroy(h); return rc; }
+  *out = h;
+  return VAQGPU_OK;
+}
+
+void hamgpu_destroy(hamgpu_t *h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_codes);
+  for (DevBuf *b : {&h->w_q, &h->w_qpad, &h->w_keys, &h->w_scratch, &h->w_stage, &h->w_idx, &h->w_dist}) b->release();
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int hamgpu_set_id_base(hamgpu_t *h, int64_t id_base) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  h->id_base = id_base;
+  return VAQGPU_OK;
+}
+
+int hamgpu_add(hamgpu_t *h, const uint64_t *words, int64_t n) {
+  if (!h || (!words && n > 0)) return fail(VAQGPU_EINVAL, "handle/words is NULL");
+  if (n < 0) return fail(VAQGPU_EINVAL, "n=%lld", (long long)n);
+  if (n == 0) return VAQGPU_OK;
+  if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index");
+  DeviceGuard g(h->device);
+  CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->W, h->n_rows + n, h->stream));
+  const int64_t chunk = std::min<int64_t>(n, kStageRows);
+  CU(h->w_stage.ensure((size_t)chunk * h->w64 * sizeof(uint64_t)));
+  for (int64_t r = 0; r < n; r += chunk) {
+    const int64_t c = std::min(chunk, n - r);
+    CU(cudaMemcpyAsync(h->w_stage.p, words + (size_t)r * h->w64, (size_t)c * h->w64 * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_ham_pack((const uint64_t *)h->w_stage.p, c, h->n_rows + r, h->w64, h->W, h->d_codes, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  h->n_rows += n;
+  return VAQGPU_OK;
+}
+
+int hamgpu_add_synthetic(hamgpu_t *h, int64_t n, uint64_t seed) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  if (n < 0) return fail(VAQGPU_EINVAL, "n=%lld", (long long)n);
+  if (n == 0) return VAQGPU_OK;
+  if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index");
+  DeviceGuard g(h->device);
+  CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->W, h->n_rows + n, h->stream));
+  CU(launch_ham_synth(h->d_codes, n, h->n_rows, h->id_base + h->n_rows, h->nbits, h->W, seed, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->n_rows += n;
+  return VAQGPU_OK;
+}
+
+int hamgpu_num_rows(const hamgpu_t *h, int64_t *n) {
+  if (!h || !n) return fail(VAQGPU_EINVAL, "handle/n is NULL");
+  *n = h->n_rows;
+  return VAQGPU_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int ham_query_impl(hamgpu_index *h, const uint64_t *d_queries, int nq, int k, int32_t *d_idx, uint32_t *d_dist,
+                   uint64_t *d_keys, cudaStream_t st) {
+  if (nq < 0 || k <= 0) return fail(VAQGPU_EINVAL, "nq=%d k=%d", nq, k);
+  if (k > 2048) return fail(VAQGPU_EINVAL, "k=%d > 2048 unsupported", k);
+  if (nq == 0) return VAQGPU_OK;
+  const int W = h->W;
+  const uint4 *dq;
+  int launches = 0;
+  if (h->w64 == 2 * W) {
+    dq = reinterpret_cast<const uint4 *>(d_queries);
+    if ((reinterpret_cast<uintptr_t>(d_queries) & 15) != 0) return fail(VAQGPU_EINVAL, "device queries must be 16-byte aligned");
+  } else {
+    CU(h->w_qpad.ensure((size_t)nq * W * sizeof(uint4)));
+    const int total = nq * W;
+    ham_pad_queries_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_queries, nq, h->w64, W, (uint4 *)h->w_qpad.p);
+    CU(cudaGetLastError());
+    dq = (const uint4 *)h->w_qpad.p;
+    launches++;
+  }
+  const int threads = kScanThreads, nwarps = threads / 32;
+  // queries per CTA: as many as the per-(warp,query) lists allow in ~64 KB
+  int qt = 8;
+  while (qt > 1 && ((size_t)nwarps * qt * k * 8 > 64 * 1024 || qt > nq)) qt >>= 1;
+  const size_t smem = (size_t)qt * W * 16 + ((size_t)nwarps * qt * k + k + qt) * sizeof(uint64_t);
+  if (smem > kSmemCap) return fail(VAQGPU_EINVAL, "k=%d needs %zu B shared memory", k, smem);
+  const int64_t n_tiles = (h->n_rows + kTileRows - 1) / kTileRows;
+  const int qgroups = (nq + qt - 1) / qt;
+  const int64_t target = (int64_t)h->num_sms * 4 * 2;
+  int splits = (int)std::max<int64_t>(1, (target + qgroups - 1) / qgroups);
+  splits = (int)std::min<int64_t>(splits, std::max<int64_t>(1, n_tiles / (nwarps * 8)));
+  CU(h->w_keys.ensure((size_t)nq * splits * k * sizeof(uint64_t)));
+  if (splits > 16) CU(h->w_scratch.ensure((size_t)2 * nq * ((splits + 15) / 16) * k * sizeof(uint64_t)));
+  CU(cudaEventRecord(h->ev[0], st));
+  HamScanArgs a{};
+  a.codes = h->d_codes; a.n_rows = h->n_rows; a.W = W; a.queries = dq;
+  a.nq = nq; a.k = k; a.splits = splits; a.qt = qt;
+  a.out_keys = (uint64_t *)h->w_keys.p;
+  CU(launch_ham_scan(a, threads, smem, st));
+  launches++;
+  CU(cudaEventRecord(h->ev[1], st));
+  CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)splits * k, splits, nq, k, 0, 1, d_idx, d_dist, d_keys, nullptr,
+                       h->id_base, (uint64_t *)h->w_scratch.p, st));
+  launches += splits > 16 ? 2 : 1;
+  CU(cudaEventRecord(h->ev[2], st));
+  h->timed = true;
+  h->cfg[0] = threads; h->cfg[1] = splits; h->cfg[2] = qt; h->cfg[3] = 0; h->cfg[4] = (int32_t)smem; h->cfg[5] = W;
+  h->cfg[6] = launches; h->cfg[7] = nq;
+  return VAQGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hamgpu_query_device(hamgpu_t *h, const uint64_t *d_queries, int32_t nq, int32_t k, int32_t *d_idx, uint32_t *d_dist,
+                        void *stream) {
+  if (!h || (nq > 0 && (!d_queries || !d_idx || !d_dist))) return fail(VAQGPU_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  return ham_query_impl(h, d_queries, nq, k, d_idx, d_dist, nullptr, (cudaStream_t)stream);
+}
+
+int hamgpu_query_keys_device(hamgpu_t *h, const uint64_t *d_queries, int32_t nq, int32_t k, uint64_t *d_keys, void *stream) {
+  if (!h || (nq > 0 && (!d_queries || !d_keys))) return fail(VAQGPU_EINVAL, "NULL argument");
+  DeviceGuard g(h->device);
+  return ham_query_impl(h, d_queries, nq, k, nullptr, nullptr, d_keys, (cudaStream_t)stream);
+}
+
+int hamgpu_merge_keys_device(const uint64_t *d_keys_in, int32_t G, int32_t nq, int32_t k, int32_t *d_idx, uint32_t *d_dist,
+                             void *stream) {
+  if (!d_keys_in || !d_idx || !d_dist) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (G < 1 || G > 16 || nq < 0 || k <= 0) return fail(VAQGPU_EINVAL, "G=%d (1..16) nq=%d k=%d", G, nq, k);
+  CU(launch_merge_keys(d_keys_in, (int64_t)nq * k, k, G, nq, k, 0, 1, d_idx, d_dist, nullptr, nullptr, 0, nullptr,
+                       (cudaStream_t)stream));
+  return VAQGPU_OK;
+}
+
+int hamgpu_query(hamgpu_t *h, const uint64_t *queries, int32_t nq, int32_t k, int32_t *idx, uint32_t *dist) {
+  if (!h || (nq > 0 && (!queries || !idx || !dist))) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (nq < 0 || k <= 0) return fail(VAQGPU_EINVAL, "nq=%d k=%d", nq, k);
+  if (nq == 0) return VAQGPU_OK;
+  DeviceGuard g(h->device);
+  CU(h->w_q.ensure((size_t)nq * h->w64 * sizeof(uint64_t)));
+  CU(h->w_idx.ensure((size_t)nq * k * sizeof(int32_t)));
+  CU(h->w_dist.ensure((size_t)nq * k * sizeof(uint32_t)));
+  CU(cudaMemcpyAsync(h->w_q.p, queries, (size_t)nq * h->w64 * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+  int rc = ham_query_impl(h, (const uint64_t *)h->w_q.p, nq, k, (int32_t *)h->w_idx.p, (uint32_t *)h->w_dist.p, nullptr, h->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(idx, h->w_idx.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(dist, h->w_dist.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VAQGPU_OK;
+}
+
+int hamgpu_last_timings(const hamgpu_t *h, float ms[2]) {
+  if (!h || !ms) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (!h->timed) return fail(VAQGPU_ESTATE, "no query has run on this handle");
+  DeviceGuard g(h->device);
+  CU(cudaEventSynchronize(h->ev[2]));
+  for (int i = 0; i < 2; i++) CU(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+  return VAQGPU_OK;
+}
+
+int hamgpu_last_config(const hamgpu_t *h, int32_t cfg[8]) {
+  if (!h || !cfg) return fail(VAQGPU_EINVAL, "NULL argument");
+  memcpy(cfg, h->cfg, sizeof(h->cfg));
+  return VAQGPU_OK;
+}
+
+}  // extern "C"

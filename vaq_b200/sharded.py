@@ -1,0 +1,112 @@
+"""Row-sharded search over the GPUs of one box: one process per GPU (torch.distributed),
+contiguous row blocks, local top-k per shard as sortable 64-bit keys, one all-gather over
+NCCL/NVLink, device-side merge (the reference's precedent for merging partial
+answers is BitVecEngine.cpp:1599-1611).
+
+The result is the k smallest (distance, id) keys overall, hence independent of the number of
+shards (bit-identical ids for G = 1, 2, 4, 8).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_rows: int, world: int) -> list[int]:
+    """Row block of rank r is [bounds[r], bounds[r+1]): ceil(n/G)-sized blocks, last one short."""
+    per = -(-int(n_rows) // int(world))
+    return [min(r * per, n_rows) for r in range(world + 1)]
+
+
+def make_keys_f32(dist: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    """(float32 distance bits << 32) | uint32 id — the key format of the scan kernels (host restatement
+    used by tests and by callers that post-process gathered keys)."""
+    d = np.ascontiguousarray(dist, np.float32).view(np.uint32).astype(np.uint64)
+    return (d << np.uint64(32)) | np.ascontiguousarray(ids).astype(np.uint32).astype(np.uint64)
+
+
+def make_keys_u32(dist: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    d = np.ascontiguousarray(dist).astype(np.uint32).astype(np.uint64)
+    return (d << np.uint64(32)) | np.ascontiguousarray(ids).astype(np.uint32).astype(np.uint64)
+
+
+def split_keys(keys: np.ndarray, hamming: bool = False):
+    keys = np.ascontiguousarray(keys, np.uint64)
+    ids = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.int32)
+    hi = (keys >> np.uint64(32)).astype(np.uint32)
+    return ids, (hi if hamming else hi.view(np.float32))
+
+
+def allgather_keys(local_keys, group=None):
+    """[nq, k] int64 tensor per rank -> [G, nq, k] on every rank (rank order == shard order)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(local_keys.shape), dtype=local_keys.dtype, device=local_keys.device)
+    if world == 1:
+        out[0].copy_(local_keys)
+    else:
+        dist.all_gather_into_tensor(out, local_keys.contiguous(), group=group)
+    return out
+
+
+class ShardedVAQ:
+    """One rank's share of a row-sharded VAQ index.  All ranks hold the same model and receive the
+    same query batch; each scans its own rows."""
+
+    def __init__(self, L, bits, centroids, eig, n_rows_total: int, rank: int, world: int, device: int, group=None):
+        from .index import VAQIndex
+        self.rank, self.world, self.group = rank, world, group
+        self.bounds = shard_bounds(n_rows_total, world)
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.index = VAQIndex(L, bits, centroids, eig=eig, device=device)
+        self.index.set_id_base(self.lo)
+        self.index.reserve(max(1, self.hi - self.lo))
+
+    def add_codes_global(self, codes: np.ndarray):
+        """Takes the full [N, M] uint16 code matrix (or any object sliceable by rows) and keeps this rank's block."""
+        self.index.add_codes(codes[self.lo:self.hi])
+
+    def add_synthetic(self, seed: int, cdf=None):
+        self.index.add_synthetic(self.hi - self.lo, seed, cdf)
+
+    def search(self, d_queries, k: int, flags: int):
+        """d_queries: CUDA float32 tensor [nq, D], identical on every rank.  Returns (labels int32 [nq,k],
+        dists float32 [nq,k]) CUDA tensors, identical on every rank."""
+        import torch
+        nq = d_queries.shape[0]
+        st = torch.cuda.current_stream().cuda_stream
+        keys = torch.empty((nq, k), dtype=torch.int64, device=d_queries.device)
+        self.index.search_keys_device(d_queries.data_ptr(), nq, k, flags, keys.data_ptr(), st)
+        allk = allgather_keys(keys, self.group)
+        labels = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
+        dists = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
+        self.index.merge_keys_device(allk.data_ptr(), self.world, nq, k, flags, labels.data_ptr(), dists.data_ptr(), st)
+        return labels, dists
+
+
+class ShardedHamming:
+    def __init__(self, nbits: int, n_rows_total: int, rank: int, world: int, device: int, group=None):
+        from .index import HammingIndex
+        self.rank, self.world, self.group = rank, world, group
+        self.bounds = shard_bounds(n_rows_total, world)
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.index = HammingIndex(nbits, device=device)
+        self.index.set_id_base(self.lo)
+
+    def add_global(self, words: np.ndarray):
+        self.index.add(words[self.lo:self.hi])
+
+    def add_synthetic(self, seed: int):
+        self.index.add_synthetic(self.hi - self.lo, seed)
+
+    def query(self, d_queries, k: int):
+        import torch
+        nq = d_queries.shape[0]
+        st = torch.cuda.current_stream().cuda_stream
+        keys = torch.empty((nq, k), dtype=torch.int64, device=d_queries.device)
+        self.index.query_keys_device(d_queries.data_ptr(), nq, k, keys.data_ptr(), st)
+        allk = allgather_keys(keys, self.group)
+        idx = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
+        dist = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
+        self.index.merge_keys_device(allk.data_ptr(), self.world, nq, k, idx.data_ptr(), dist.data_ptr(), st)
+        return idx, dist

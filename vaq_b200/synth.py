@@ -67,3 +67,68 @@ def recall_at_k(labels: np.ndarray, gt: np.ndarray, k: int) -> float:
     for i in range(labels.shape[0]):
         hits += len(set(labels[i].tolist()) & set(gt[i, :k].tolist()))
     return hits / (labels.shape[0] * k)
+
+
+# ---- counter-based generators restated from the device kernels (vaq_b200/csrc/pack.cu
+# synth_codes_kernel, hamming_scan.cu ham_synth_kernel) so any row slice of a 100M / 1B-row
+# on-device index can be regenerated on the host for parity checks.
+_G1 = np.uint64(0x9E3779B97F4A7C15)
+_G2 = np.uint64(0xD1B54A32D192ED03)
+
+
+def _mix64(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint64, copy=True)
+    x ^= x >> np.uint64(30)
+    x *= np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(27)
+    x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    return x
+
+
+def synth_codes(bits, n: int, row0: int, seed: int, cdf=None) -> np.ndarray:
+    """[n, M] uint16 codes of global rows [row0, row0+n) exactly as vaqgpu_add_codes_synthetic makes them."""
+    bits = np.asarray(bits, np.int64)
+    M = bits.size
+    rows = (np.arange(n, dtype=np.uint64) + np.uint64(row0))[:, None]
+    subs = np.arange(M, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        h = _mix64(np.uint64(seed) ^ (rows * _G1 + subs * _G2))
+    top = (h >> np.uint64(40)).astype(np.uint32)
+    K = (1 << bits)
+    if cdf is None:
+        return (top & (K - 1).astype(np.uint32)[None, :]).astype(np.uint16)
+    cdf = np.asarray(cdf, np.float32)
+    off = np.concatenate([[0], np.cumsum(K)])
+    u = top.astype(np.float32) * np.float32(1.0 / 16777216.0)
+    out = np.empty((n, M), np.uint16)
+    for s in range(M):
+        t = cdf[off[s]:off[s + 1]]
+        out[:, s] = np.minimum(np.searchsorted(t, u[:, s], side="right"), K[s] - 1).astype(np.uint16)
+    return out
+
+
+def synth_bitvectors(n: int, row0: int, nbits: int, seed: int) -> np.ndarray:
+    """[n, ceil(nbits/64)] uint64 words of global rows [row0, row0+n) as hamgpu_add_synthetic makes them."""
+    w64 = (nbits + 63) // 64
+    rows = (np.arange(n, dtype=np.uint64) + np.uint64(row0))[:, None]
+    ws = np.arange(w64, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        x = _mix64(np.uint64(seed) ^ (rows * _G1 + ws * _G2))
+    rem = nbits - (w64 - 1) * 64
+    if rem < 64:
+        x[:, -1] &= np.uint64((1 << rem) - 1)
+    return np.ascontiguousarray(x)
+
+
+def code_cdf(codes: np.ndarray, bits) -> np.ndarray:
+    """Empirical per-subspace cumulative code distribution (concatenated, last entry of each table = 1)."""
+    bits = np.asarray(bits, np.int64)
+    out = []
+    for s in range(bits.size):
+        K = 1 << int(bits[s])
+        cnt = np.bincount(codes[:, s].astype(np.int64), minlength=K).astype(np.float64)
+        c = np.cumsum(cnt) / cnt.sum()
+        c[-1] = 1.0
+        out.append(c.astype(np.float32))
+    return np.concatenate(out)
