@@ -40,7 +40,7 @@ def allgather_keys(local_keys, group=None):
     """[nq, k] int64 tensor per rank -> [G, nq, k] on every rank (rank order == shard order)."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     out = torch.empty((world,) + tuple(local_keys.shape), dtype=local_keys.dtype, device=local_keys.device)
     if world == 1:
         out[0].copy_(local_keys)
