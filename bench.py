@@ -210,7 +210,7 @@ def run_gpu_arm(args, w, name):
 
     model, X, XP, Qraw, Q = build_problem(w)
     n, nq, k = w["n"], w["nq"], w["k"]
-    flags = EA | PROJECTED
+    flags = EA | PROJECTED | (0x1000 if args.scan_v1 else 0)
 
     # index: this rank's row block, encoded on the device (bit-exact vs the oracle, tests/test_gpu_vaq.py)
     sh = ShardedVAQ(model.L, model.bits, model.centroids, model.eig, n, rank, world, local_rank)
@@ -297,16 +297,19 @@ def run_gpu_arm(args, w, name):
     row_bytes = ix.row_bytes
     lut_bytes = int(ix.lut_size) * 4
     n_launch = -(-nq // cfg["queries_per_launch"])
-    alg_bytes_step = nq * (n_local * row_bytes + lut_bytes + k * 8 * cfg["splits"])
+    T = max(1, cfg["queries_per_cta"])
+    # one pass over the local rows per query TILE (T queries share the stream) + per-query LUT and result bytes
+    alg_bytes_step = -(-nq // T) * n_local * row_bytes + nq * (lut_bytes + k * 8 * cfg["row_chunks"])
     scan_ms_mean = float(np.mean(scan_ms))
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes_step / (scan_ms_mean / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "adc_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
-                "launch_ms": scan_ms_mean / n_launch, "query_tile_T": 1,
-                "note": ("T=1 accounting (SURVEY 8d): every query streams all local rows; at this shape the packed codes "
-                         f"({n_local * row_bytes / 1e6:.0f} MB) are L2-resident, so DRAM traffic is far below the algorithmic bytes — "
-                         "see roofline_hbm_shape for the same kernel on a shard >> L2")}
+                "launch_ms": scan_ms_mean / n_launch, "query_tile_T": T,
+                "pairs_per_s": nq * n_local / (scan_ms_mean / 1e3),
+                "note": ("SURVEY 8d accounting: ceil(nq/T) passes over the packed rows (T queries share each pass) + LUT/result bytes; "
+                         f"at this shape the packed codes ({n_local * row_bytes / 1e6:.0f} MB) are L2-resident and the scan is bound by "
+                         "shared-memory LUT gathers, not HBM — see roofline_hbm_shape for the same kernel on a shard >> L2")}
 
     # ---- the same kernel on a shard far larger than L2 (the HBM-bound regime of the 100M / 1B-row shapes)
     hbm_shape = None
@@ -326,11 +329,13 @@ def run_gpu_arm(args, w, name):
                 torch.cuda.synchronize()
                 if i >= 3:
                     ms.append(big.last_timings()["scan_ms"])
-            b = bq * (big_n * row_bytes + lut_bytes)
+            bcfg = big.last_config()
+            bT = max(1, bcfg["queries_per_cta"])
+            b = -(-bq // bT) * big_n * row_bytes + bq * lut_bytes
             a = b / (np.mean(ms) / 1e3) / 1e9
             hbm_shape = {"rows": big_n, "queries": bq, "packed_bytes": big_n * row_bytes, "scan_ms": float(np.mean(ms)),
-                         "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "query_tile_T": 1,
-                         "config": big.last_config()}
+                         "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "query_tile_T": bT,
+                         "pairs_per_s": bq * big_n / (np.mean(ms) / 1e3), "config": bcfg}
             big.close()
         except Exception as e:      # never hide the headline behind the auxiliary leg
             hbm_shape = {"error": repr(e)}
@@ -387,6 +392,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hbm-shape", action="store_true")
     ap.add_argument("--hbm-rows", type=int, default=64_000_000)
+    ap.add_argument("--scan-v1", action="store_true", help="force the lane-per-row scan kernel (comparison)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]

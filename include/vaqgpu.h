@@ -43,6 +43,7 @@ extern "C" {
 #define VAQGPU_HEAP 0x80u       /* exhaustive scan (searchHeap, VAQ.cpp:1729) */
 #define VAQGPU_PROJECTED 0x100u /* queries are already in PCA space: skip (X*V).real(), VAQ.cpp:777 */
 #define VAQGPU_SQRT 0x200u      /* return sqrt(ADC) as the TI mode does (VAQ.cpp:1585) */
+#define VAQGPU_SCAN_V1 0x1000u  /* diagnostics: force the lane-per-row scan kernel for EA searches */
 
 typedef struct vaqgpu_index vaqgpu_t;
 typedef struct hamgpu_index hamgpu_t;
@@ -138,10 +139,11 @@ int vaqgpu_refine(vaqgpu_t *h, const float *queries, int32_t nq, const int32_t *
 /* Timing of the kernels of the last search on this handle, in milliseconds (CUDA events on
  * the launching stream): [0]=projection, [1]=LUT build, [2]=ADC scan, [3]=merge/output. */
 int vaqgpu_last_timings(const vaqgpu_t *h, float ms[4]);
-/* Scan configuration chosen for the last search: [0]=threads/CTA, [1]=CTAs (splits) per query,
- * [2]=LUT floats resident in shared memory, [3]=LUT floats spilled to L2, [4]=dynamic smem bytes,
- * [5]=uint4 words per row, [6]=kernel launches of the last search, [7]=queries per launch. */
-int vaqgpu_last_config(const vaqgpu_t *h, int32_t cfg[8]);
+/* Scan configuration chosen for the last search: [0]=threads/CTA, [1]=row chunks (CTAs per query tile),
+ * [2]=LUT entries per query resident in shared memory, [3]=LUT entries spilled to L2, [4]=dynamic smem
+ * bytes, [5]=uint4 words per row, [6]=kernel launches of the last search, [7]=queries per launch,
+ * [8]=queries per CTA (tile width T), [9]=scan kernel (1 = lane-per-row, 2 = filter-and-refine). */
+int vaqgpu_last_config(const vaqgpu_t *h, int32_t cfg[12]);
 
 /* ---- BitVecEngine Hamming index ---------------------------------------- */
 

@@ -129,10 +129,14 @@ def check_search(port, m, codes, Q, k, flags, ix=None, id_base=0):
         ix = make_index(m, codes=codes)
         if id_base:
             ix.set_id_base(id_base)
-    lab, dis = ix.search(Q, k, flags | PROJECTED)
+    from vaq_b200.index import SCAN_V1
     want_lab, want_dis = port.search_lex(m, codes, Q, k, id_base)
-    assert np.array_equal(lab, want_lab), "ids differ from the canonical (distance, id) top-k"
-    assert bitwise_equal(dis, want_dis), "distances are not bit-identical to the oracle's summation order"
+    for extra, kern in ((0, None), (SCAN_V1, 1)):       # default kernel choice, then the lane-per-row kernel
+        lab, dis = ix.search(Q, k, flags | PROJECTED | extra)
+        assert np.array_equal(lab, want_lab), f"ids differ from the canonical (distance, id) top-k (extra={extra:#x})"
+        assert bitwise_equal(dis, want_dis), "distances are not bit-identical to the oracle's summation order"
+        if kern:
+            assert ix.last_config()["scan_kernel"] == kern
     if own:
         ix.close()
     return lab, dis
@@ -177,6 +181,34 @@ def test_search_ragged_sizes(port, n, k, mode):
         assert (dis[:, n:] == np.finfo(np.float32).max).all()
 
 
+@pytest.mark.parametrize("nq", [1, 2, 3, 4, 5, 7, 8, 9, 17])
+@pytest.mark.parametrize("bits", [[6, 6, 5, 5], [9, 8, 8, 7, 6, 6, 5, 4], [11, 11, 10, 10, 9, 9, 8, 8, 7, 7, 7, 7, 6, 6, 6, 6]])
+def test_search_query_tile_shapes(port, nq, bits):
+    """Partial query tiles (nq not a multiple of T) and every tile width the planner can pick."""
+    from vaq_b200.index import EA
+    rng = np.random.default_rng(nq * 100 + len(bits))
+    m = random_model(rng, len(bits), 2, bits)
+    codes = random_codes(rng, m, 9000)
+    Q = rng.standard_normal((nq, m.D)).astype(np.float32)
+    check_search(port, m, codes, Q, 10, EA)
+
+
+def test_search_multi_chunk_and_large_k(port):
+    """Few queries on many rows -> several row chunks per query tile, thresholds carried between chunks."""
+    from vaq_b200.index import EA, PROJECTED
+    rng = np.random.default_rng(99)
+    m = random_model(rng, 8, 4, [9, 8, 8, 7, 6, 6, 5, 4])
+    codes = random_codes(rng, m, 300000)
+    Q = rng.standard_normal((3, m.D)).astype(np.float32) * 2
+    ix = make_index(m, codes=codes)
+    check_search(port, m, codes, Q, 10, EA, ix=ix)
+    ix.search(Q, 10, EA | PROJECTED)
+    assert ix.last_config()["row_chunks"] > 1
+    check_search(port, m, codes, Q, 300, EA, ix=ix)
+    check_search(port, m, codes, Q[:1], 1500, EA, ix=ix)
+    ix.close()
+
+
 def test_search_duplicate_rows_tie_rule(port):
     """Exact ties: every row repeated 4x -> canonical order keeps the lowest ids."""
     from vaq_b200.index import EA
@@ -206,10 +238,13 @@ def test_search_spill_path(port):
     codes = random_codes(rng, m, 50000)
     Q = rng.standard_normal((6, m.D)).astype(np.float32)
     ix = make_index(m, codes=codes)
+    from vaq_b200.index import PROJECTED
     check_search(port, m, codes, Q, 10, EA, ix=ix)
+    ix.search(Q, 10, EA | PROJECTED)
     cfg = ix.last_config()
-    assert cfg["spill_lut_floats"] > 0, cfg
+    assert cfg["spill_lut_floats"] > 0 and cfg["scan_kernel"] == 2, cfg
     check_search(port, m, codes, Q, 10, HEAP, ix=ix)
+    assert ix.last_config()["spill_lut_floats"] > 0
     ix.close()
 
 

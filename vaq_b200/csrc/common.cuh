@@ -22,12 +22,15 @@ struct ScanLayout {
   int32_t W;                          // uint4 words per row
   uint16_t fbeg[kMaxRowWords + 1];    // fields starting in word w: [fbeg[w], fbeg[w+1])
   uint32_t fmeta[kMaxSubspaces];      // see above
-  uint32_t foff[kMaxSubspaces];       // float offset of table s inside the smem LUT or the spill area
+  uint32_t foff[kMaxSubspaces];       // entry offset of table s inside the smem LUT or the spill area
+  uint8_t fword[kMaxSubspaces];       // 32-bit word in which field s starts
 };
 
 // Where the LUT build kernel writes table s inside a query's LUT row.
 struct LutPlan {
   int32_t M, L;
+  int32_t T;                          // query-tile interleave: entry e of query q lives at
+                                      //   ((q / T) * row_stride + pos + e) * T + q % T
   int32_t total_entries;              // sum K_s
   int32_t row_stride;                 // floats per query row in the LUT workspace
   int32_t ent_off[kMaxSubspaces + 1]; // compact entry offsets (prefix sum of K_s)
@@ -166,8 +169,27 @@ struct AdcScanArgs {
 cudaError_t launch_adc_scan(const AdcScanArgs &a, int threads, size_t smem_bytes, cudaStream_t st);
 cudaError_t adc_scan_occupancy(int W, int threads, size_t smem_bytes, int *ctas_per_sm);
 
-cudaError_t launch_lut_build(const float *q_proj, int nq, int D, const float *centroids, const LutPlan &plan,
-                             float *lut, cudaStream_t st);
+// filter-and-refine scan (adc_filter_scan.cu)
+struct AdcFilterArgs {
+  const uint4 *codes;        // packed tiles [tile][w][lane]
+  int64_t n_rows;
+  const float *lut;          // interleaved LUT workspace [query tile][row_stride][T]
+  int32_t lut_stride;        // entries per query (row_stride)
+  int32_t smem_lut_floats;   // resident entries per query (multiple of 4)
+  int32_t nq, k;
+  int32_t chunk_tiles;       // 32-row tiles per row chunk
+  int32_t n_chunks;
+  uint64_t *out_keys;        // [nq][n_chunks][k]; low word = LOCAL row index
+  uint32_t *thr_global;      // [nq] float bits of the best known k-th distance (0xFFFFFFFF = none)
+  ScanLayout lay;
+};
+size_t adc_filter_smem_bytes(int smem_lut_floats, int T, int k, int threads);
+cudaError_t launch_adc_filter_scan(const AdcFilterArgs &a, int T, int threads, size_t smem_bytes, cudaStream_t st);
+cudaError_t launch_fill_u32(uint32_t *p, int n, uint32_t v, cudaStream_t st);
+
+// nq_launch >= nq queries are written (tile padding repeats the last query)
+cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, const float *centroids,
+                             const LutPlan &plan, float *lut, cudaStream_t st);
 cudaError_t launch_project(const float *x, int n, int D, const float *eig, float *out, cudaStream_t st);
 
 cudaError_t launch_pack_codes(const uint16_t *codes, int64_t n, int64_t row0, const ScanLayout &lay, uint4 *packed,

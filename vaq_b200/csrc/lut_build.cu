@@ -54,11 +54,12 @@ __device__ __forceinline__ float l2sqr_small(const float *__restrict__ x, const 
   }
 }
 
-__global__ void lut_build_kernel(const float *__restrict__ q_proj, int D, const float *__restrict__ cent,
+__global__ void lut_build_kernel(const float *__restrict__ q_proj, int nq, int D, const float *__restrict__ cent,
                                  const __grid_constant__ LutPlan p, float *__restrict__ lut) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.total_entries) return;
-  const int q = blockIdx.y;
+  const int qo = blockIdx.y;            // output slot; slots past nq (tile padding) repeat the last query
+  const int q = min(qo, nq - 1);
   int lo = 0, hi = p.M;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -80,15 +81,15 @@ __global__ void lut_build_kernel(const float *__restrict__ q_proj, int D, const 
   } else {
     acc = l2sqr_small(qs, cp, L);
   }
-  lut[(size_t)q * p.row_stride + p.pos[s] + c] = acc;
+  lut[((size_t)(qo / p.T) * p.row_stride + p.pos[s] + c) * p.T + (qo % p.T)] = acc;
 }
 
-cudaError_t launch_lut_build(const float *q_proj, int nq, int D, const float *centroids, const LutPlan &plan,
-                             float *lut, cudaStream_t st) {
+cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, const float *centroids,
+                             const LutPlan &plan, float *lut, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   const int threads = 256;
-  dim3 grid((unsigned)((plan.total_entries + threads - 1) / threads), (unsigned)nq);
-  lut_build_kernel<<<grid, threads, 0, st>>>(q_proj, D, centroids, plan, lut);
+  dim3 grid((unsigned)((plan.total_entries + threads - 1) / threads), (unsigned)nq_launch);
+  lut_build_kernel<<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut);
   return cudaGetLastError();
 }
 

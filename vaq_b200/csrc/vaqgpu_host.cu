@@ -87,7 +87,6 @@ struct vaqgpu_index {
 
   ScanLayout lay{};
   LutPlan plan{};
-  int32_t smem_lut_floats = 0, spill_floats = 0;
 
   float *d_centroids = nullptr;
   float *d_eig = nullptr;
@@ -110,9 +109,9 @@ struct vaqgpu_index {
   cudaStream_t stream = nullptr;   // used by the host-buffer entry points
   cudaEvent_t ev[5] = {};
   bool timed = false;
-  int32_t cfg[8] = {};
+  int32_t cfg[12] = {};
 
-  DevBuf w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
+  DevBuf w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
 };
 
 struct hamgpu_index {
@@ -195,36 +194,42 @@ int plan_model(vaqgpu_index *h) {
   }
   lay.fbeg[4 * W] = (uint16_t)M;
 
-  // LUT residency: tables are taken in scan order (variance-descending — with early abandon the
-  // leading tables are the ones every row touches) while they fit the shared-memory budget; the
-  // rest stay in global memory and are served by L1/L2.
-  const size_t list_reserve = 24 * 1024;    // top-k lists, merge buffer, barrier
-  const size_t budget_floats = (kSmemCap - list_reserve) / 4;
-  // if everything fits in half the SM, keep it all (two CTAs per SM); otherwise fill one CTA's budget
+  for (int s = 0; s < M; s++) lay.fword[s] = (uint8_t)word_of[s];
+  plan.T = 1;
+  return VAQGPU_OK;
+}
+
+// LUT residency for a given shared-memory budget (entries per query): tables are taken in scan order
+// (variance-descending — with early abandon the leading tables are the ones every row touches)
+// while they fit; the rest stay in global memory and are served by L1/L2 ("spill").
+void apply_residency(const vaqgpu_index *h, size_t budget_entries, int T, ScanLayout &lay, LutPlan &plan, int32_t &res_floats,
+                     int32_t &spill_floats) {
+  const int M = h->M;
+  lay = h->lay;
+  plan = h->plan;
+  plan.T = T;
   size_t resident = 0;
   std::vector<char> res(M, 0);
   for (int s = 0; s < M; s++) {
     const size_t K = (size_t)1 << h->bits[s];
-    if (resident + K <= budget_floats) { res[s] = 1; resident += K; }
+    if (resident + K <= budget_entries) { res[s] = 1; resident += K; }
   }
   int32_t pos = 0;
   for (int s = 0; s < M; s++)
     if (res[s]) { plan.pos[s] = pos; lay.foff[s] = (uint32_t)pos; pos += 1 << h->bits[s]; }
-  const int32_t res_floats = (pos + 3) & ~3;
+  res_floats = (pos + 3) & ~3;
   int32_t sp = 0;
   for (int s = 0; s < M; s++)
     if (!res[s]) {
       plan.pos[s] = res_floats + sp; lay.foff[s] = (uint32_t)sp; lay.fmeta[s] |= kFieldSpill; sp += 1 << h->bits[s];
     }
-  h->smem_lut_floats = res_floats;
-  h->spill_floats = sp;
+  spill_floats = sp;
   plan.row_stride = (res_floats + sp + 3) & ~3;
-  return VAQGPU_OK;
 }
 
-size_t scan_smem_bytes(const vaqgpu_index *h, int k, int threads) {
+size_t scan_smem_bytes(int smem_lut_floats, int k, int threads) {
   const int nwarps = threads / 32;
-  size_t b = (((size_t)h->smem_lut_floats * 4 + 15) & ~(size_t)15);
+  size_t b = (((size_t)smem_lut_floats * 4 + 15) & ~(size_t)15);
   b += ((size_t)nwarps * k + k + 2) * sizeof(uint64_t);
   return b;
 }
@@ -246,6 +251,12 @@ __global__ void ham_pad_queries_kernel(const uint64_t *__restrict__ q, int nq, i
 }
 
 // The whole device-side search; exactly one of (d_labels,d_dists) / d_keys is the output.
+//
+// Scan kernel selection (the reference dispatches TI -> EA -> HEAP, VAQ.cpp:799-840):
+//   EA (default)     -> adc_filter_scan_kernel: stage-1 filter on the first group + exact stage 2
+//   HEAP             -> adc_scan_kernel without abandoning (exhaustive, as searchHeap)
+//   TI / visit       -> adc_scan_kernel over per-query row ranges, with abandoning
+//   VAQGPU_SCAN_V1   -> force adc_scan_kernel (lane-per-row, warp-uniform abandoning)
 int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, uint32_t flags, int32_t *d_labels,
                        float *d_dists, uint64_t *d_keys, cudaStream_t st, bool record) {
   if (nq < 0 || k <= 0) return fail(VAQGPU_EINVAL, "nq=%d k=%d", nq, k);
@@ -255,11 +266,9 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   if (!projected && !h->d_eig) return fail(VAQGPU_ESTATE, "raw queries need eig_real in the model (or pass VAQGPU_PROJECTED)");
   const bool ti = (flags & VAQGPU_TI) != 0;
   if (ti && !h->d_clusters) return fail(VAQGPU_ESTATE, "VAQGPU_TI needs vaqgpu_set_clusters");
-  // the reference dispatches TI -> EA -> HEAP (VAQ.cpp:799-840); HEAP alone is the exhaustive scan
   const bool ea = (flags & VAQGPU_EA) != 0 || ti || !(flags & VAQGPU_HEAP);
-  const int threads = kScanThreads;
-  const size_t smem = scan_smem_bytes(h, k, threads);
-  if (smem > kSmemCap) return fail(VAQGPU_EINVAL, "k=%d needs %zu B shared memory (> %zu)", k, smem, kSmemCap);
+  const bool filter = ea && !ti && !(flags & VAQGPU_SCAN_V1) && h->n_rows > 0;
+  const bool want_sqrt = (flags & VAQGPU_SQRT) != 0;
   int launches = 0;
 
   if (record) CU(cudaEventRecord(h->ev[0], st));
@@ -272,12 +281,95 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   }
   if (record) CU(cudaEventRecord(h->ev[1], st));
 
-  int ctas_per_sm = 1;
-  CU(adc_scan_occupancy(h->lay.W, threads, smem, &ctas_per_sm));
-  if (ctas_per_sm < 1) return fail(VAQGPU_ECUDA, "ADC scan kernel does not fit an SM with %zu B shared memory", smem);
   const int64_t n_tiles = (h->n_rows + kTileRows - 1) / kTileRows;
+  ScanLayout lay;
+  LutPlan plan;
+  int32_t res_floats = 0, spill_floats = 0;
+
+  if (filter) {
+    // ---- query-tile width T and residency -------------------------------------------------------
+    int threads = 512;
+    int T = nq >= 8 ? 8 : (nq >= 3 ? 4 : nq);
+    for (;; T >>= 1) {
+      const size_t fixed = adc_filter_smem_bytes(0, T, k, threads) + 1024;
+      if (fixed < kSmemCap) {
+        const size_t budget = (kSmemCap - fixed) / (4 * (size_t)T);
+        if ((size_t)h->total_entries + 4 <= budget || T == 1) {
+          apply_residency(h, budget, T, lay, plan, res_floats, spill_floats);
+          break;
+        }
+      }
+      if (T == 1) {
+        threads >>= 1;
+        if (threads < 64) return fail(VAQGPU_EINVAL, "k=%d does not fit the scan's shared memory", k);
+        T = 2;   // retry T=1 with fewer warps (fewer per-warp lists)
+      }
+    }
+    const size_t smem = adc_filter_smem_bytes(res_floats, T, k, threads);
+    if (smem > kSmemCap) return fail(VAQGPU_EINVAL, "k=%d needs %zu B shared memory (> %zu)", k, smem, kSmemCap);
+    const int nwarps = threads / 32;
+    const size_t bytes_per_q = (size_t)plan.row_stride * 4;
+    int qb_max = (int)std::max<size_t>(T, std::min<size_t>((size_t)nq, kLutWorkspaceBytes / bytes_per_q));
+    qb_max = (qb_max + T - 1) / T * T;
+    // ---- row chunks: enough CTAs to fill the machine, chunks small enough to stay L2-resident while
+    // every query tile sweeps them (query tiles are the fast grid dimension)
+    const int qtiles_first = (std::min(nq, qb_max) + T - 1) / T;
+    const int64_t target = (int64_t)h->num_sms * 3;
+    int64_t n_chunks = std::max<int64_t>(1, (target + qtiles_first - 1) / qtiles_first);
+    n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16)));
+    n_chunks = std::max<int64_t>(n_chunks, (n_tiles + 32767) / 32768);          // <= 1M rows per chunk
+    int64_t chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
+    n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+    if (n_chunks > 65535) return fail(VAQGPU_EINVAL, "index too large for one launch (%lld chunks)", (long long)n_chunks);
+
+    CU(h->w_lut.ensure((size_t)qb_max * bytes_per_q));
+    CU(h->w_keys.ensure((size_t)qb_max * n_chunks * k * sizeof(uint64_t)));
+    CU(h->w_thr.ensure((size_t)qb_max * sizeof(uint32_t)));
+    if (n_chunks > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((n_chunks + 15) / 16) * k * sizeof(uint64_t)));
+
+    for (int q0 = 0; q0 < nq; q0 += qb_max) {
+      const int qb = std::min(qb_max, nq - q0);
+      const int qb_pad = (qb + T - 1) / T * T;
+      const float *qp = d_qproj + (size_t)q0 * h->D;
+      CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, plan, (float *)h->w_lut.p, st));
+      CU(launch_fill_u32((uint32_t *)h->w_thr.p, qb, 0xFFFFFFFFu, st));
+      launches += 2;
+      if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
+      AdcFilterArgs a{};
+      a.codes = h->d_codes; a.n_rows = h->n_rows;
+      a.lut = (const float *)h->w_lut.p; a.lut_stride = plan.row_stride; a.smem_lut_floats = res_floats;
+      a.nq = qb; a.k = k; a.chunk_tiles = (int32_t)chunk_tiles; a.n_chunks = (int32_t)n_chunks;
+      a.out_keys = (uint64_t *)h->w_keys.p;
+      a.thr_global = (uint32_t *)h->w_thr.p;
+      a.lay = lay;
+      CU(launch_adc_filter_scan(a, T, threads, smem, st));
+      launches++;
+      if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
+      CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)n_chunks * k, (int)n_chunks, qb, k, want_sqrt ? 1 : 0, 0,
+                           d_labels ? d_labels + (size_t)q0 * k : nullptr, d_dists ? (void *)(d_dists + (size_t)q0 * k) : nullptr,
+                           d_keys ? d_keys + (size_t)q0 * k : nullptr, nullptr, h->id_base, (uint64_t *)h->w_scratch.p, st));
+      launches += n_chunks > 16 ? 2 : 1;
+    }
+    if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
+    h->cfg[0] = threads; h->cfg[1] = (int32_t)n_chunks; h->cfg[2] = res_floats; h->cfg[3] = spill_floats;
+    h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
+    h->cfg[8] = T; h->cfg[9] = 2;
+    return VAQGPU_OK;
+  }
+
+  // ---- lane-per-row kernel (HEAP / TI / forced) ---------------------------------------------------
+  const int threads = kScanThreads;
+  {
+    const size_t fixed = scan_smem_bytes(0, k, threads) + 1024;
+    if (fixed >= kSmemCap) return fail(VAQGPU_EINVAL, "k=%d needs more shared memory than an SM has", k);
+    apply_residency(h, (kSmemCap - fixed) / 4, 1, lay, plan, res_floats, spill_floats);
+  }
+  const size_t smem = scan_smem_bytes(res_floats, k, threads);
+  int ctas_per_sm = 1;
+  CU(adc_scan_occupancy(lay.W, threads, smem, &ctas_per_sm));
+  if (ctas_per_sm < 1) return fail(VAQGPU_ECUDA, "ADC scan kernel does not fit an SM with %zu B shared memory", smem);
   const int nwarps = threads / 32;
-  const int qb_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)nq, kLutWorkspaceBytes / ((size_t)h->plan.row_stride * 4)));
+  const int qb_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)nq, kLutWorkspaceBytes / ((size_t)plan.row_stride * 4)));
   // CTAs per query: fill ~2 waves of the machine when there are few queries, but leave each
   // warp at least 8 tiles so the per-CTA LUT staging stays amortised.
   const int64_t target = (int64_t)h->num_sms * ctas_per_sm * 2;
@@ -286,7 +378,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   splits = (int)std::min<int64_t>(splits, max_splits);
   if (ti) splits = std::min(splits, 4);
 
-  CU(h->w_lut.ensure((size_t)qb_max * h->plan.row_stride * sizeof(float)));
+  CU(h->w_lut.ensure((size_t)qb_max * plan.row_stride * sizeof(float)));
   CU(h->w_keys.ensure((size_t)qb_max * splits * k * sizeof(uint64_t)));
   if (splits > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((splits + 15) / 16) * k * sizeof(uint64_t)));
   if (ti) {
@@ -302,23 +394,22 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
                               (int2 *)h->w_ranges.p, (int32_t *)h->w_nranges.p, st));
       launches++;
     }
-    CU(launch_lut_build(qp, qb, h->D, h->d_centroids, h->plan, (float *)h->w_lut.p, st));
+    CU(launch_lut_build(qp, qb, qb, h->D, h->d_centroids, plan, (float *)h->w_lut.p, st));
     launches++;
     if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
     AdcScanArgs a{};
     a.codes = h->d_codes; a.n_rows = h->n_rows;
-    a.lut = (const float *)h->w_lut.p; a.lut_stride = h->plan.row_stride;
-    a.smem_lut_floats = h->smem_lut_floats;
+    a.lut = (const float *)h->w_lut.p; a.lut_stride = plan.row_stride;
+    a.smem_lut_floats = res_floats;
     a.nq = qb; a.k = k; a.splits = splits;
     a.early_abandon = ea ? 1 : 0;
     a.use_tma = 1;
     a.out_keys = (uint64_t *)h->w_keys.p;
     if (ti) { a.ranges = (const int2 *)h->w_ranges.p; a.n_ranges = (const int32_t *)h->w_nranges.p; a.max_ranges = h->C; }
-    a.lay = h->lay;
+    a.lay = lay;
     CU(launch_adc_scan(a, threads, smem, st));
     launches++;
     if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
-    const bool want_sqrt = (flags & VAQGPU_SQRT) != 0;
     CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)splits * k, splits, qb, k, want_sqrt ? 1 : 0, 0,
                          d_labels ? d_labels + (size_t)q0 * k : nullptr, d_dists ? (void *)(d_dists + (size_t)q0 * k) : nullptr,
                          d_keys ? d_keys + (size_t)q0 * k : nullptr, ti ? h->d_id_map : nullptr, h->id_base,
@@ -326,8 +417,9 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     launches += splits > 16 ? 2 : 1;
   }
   if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
-  h->cfg[0] = threads; h->cfg[1] = splits; h->cfg[2] = h->smem_lut_floats; h->cfg[3] = h->spill_floats;
-  h->cfg[4] = (int32_t)smem; h->cfg[5] = h->lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
+  h->cfg[0] = threads; h->cfg[1] = splits; h->cfg[2] = res_floats; h->cfg[3] = spill_floats;
+  h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
+  h->cfg[8] = 1; h->cfg[9] = 1;
   return VAQGPU_OK;
 }
 
@@ -404,7 +496,7 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   cudaFree(h->d_centroids); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
   cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size);
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
-  for (DevBuf *b : {&h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
+  for (DevBuf *b : {&h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
                     &h->w_labels, &h->w_dists, &h->w_outkeys, &h->w_cdf, &h->w_x})
     b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -539,12 +631,13 @@ int vaqgpu_build_lut(vaqgpu_t *h, const float *q_proj, int32_t nq, float *lut_ou
   DeviceGuard g(h->device);
   // compact plan: table s at ent_off[s]
   LutPlan p = h->plan;
+  p.T = 1;
   for (int s = 0; s < h->M; s++) p.pos[s] = p.ent_off[s];
   p.row_stride = p.total_entries;
   CU(h->w_q.ensure((size_t)nq * h->D * sizeof(float)));
   CU(h->w_lut.ensure((size_t)nq * p.row_stride * sizeof(float)));
   CU(cudaMemcpyAsync(h->w_q.p, q_proj, (size_t)nq * h->D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  CU(launch_lut_build((const float *)h->w_q.p, nq, h->D, h->d_centroids, p, (float *)h->w_lut.p, h->stream));
+  CU(launch_lut_build((const float *)h->w_q.p, nq, nq, h->D, h->d_centroids, p, (float *)h->w_lut.p, h->stream));
   CU(cudaMemcpyAsync(lut_out, h->w_lut.p, (size_t)nq * p.row_stride * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return VAQGPU_OK;
@@ -664,7 +757,7 @@ int vaqgpu_last_timings(const vaqgpu_t *h, float ms[4]) {
   return VAQGPU_OK;
 }
 
-int vaqgpu_last_config(const vaqgpu_t *h, int32_t cfg[8]) {
+int vaqgpu_last_config(const vaqgpu_t *h, int32_t cfg[12]) {
   if (!h || !cfg) return fail(VAQGPU_EINVAL, "NULL argument");
   memcpy(cfg, h->cfg, sizeof(h->cfg));
   return VAQGPU_OK;

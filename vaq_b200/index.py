@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import EA, HEAP, PROJECTED, SQRT, TI, ModelDesc, check  # noqa: F401 (re-exported)
+from ._lib import EA, HEAP, PROJECTED, SCAN_V1, SQRT, TI, ModelDesc, check  # noqa: F401 (re-exported)
 
 
 def _c(a, dtype):
@@ -174,10 +174,10 @@ class VAQIndex:
         return dict(project_ms=ms[0], lut_ms=ms[1], scan_ms=ms[2], merge_ms=ms[3])
 
     def last_config(self) -> dict:
-        cfg = (C.c_int32 * 8)()
+        cfg = (C.c_int32 * 12)()
         check(self.lib.vaqgpu_last_config(self.h, cfg))
-        keys = ["threads", "splits", "smem_lut_floats", "spill_lut_floats", "smem_bytes", "row_words", "launches",
-                "queries_per_launch"]
+        keys = ["threads", "row_chunks", "smem_lut_floats", "spill_lut_floats", "smem_bytes", "row_words", "launches",
+                "queries_per_launch", "queries_per_cta", "scan_kernel"]
         return dict(zip(keys, list(cfg)))
 
 
