@@ -27,8 +27,6 @@
 
 namespace vaqgpu {
 
-constexpr int kQueueCap = 64;   // per-warp survivor queue (worst case 31 pending + 32 pushed)
-constexpr int kPrefetch = 3;    // tiles in flight per warp
 
 template <int T> struct LutVec;
 template <> struct LutVec<1> { float v[1]; };
@@ -85,67 +83,63 @@ __device__ __forceinline__ void lds_thr(float (&out)[T], const uint32_t *p) {
   }
 }
 
-// Full-precision score of one (row, query) pair per lane; returns false when every lane abandoned.
-template <int W, int T>
-__device__ __forceinline__ bool score_pair(const uint4 (&cw)[W], const ScanLayout &lay, const float *__restrict__ slut,
+// Full-precision score of one (row, query) pair per lane, all subspaces in the reference's order and
+// grouping (dism = ((l0+l1)+l2)+l3 ; dist += dism, VAQ.cpp:1741-1748).  The row's 32-bit words are
+// fetched through L1 as the walk needs them (each lane has a different row, so there is nothing to
+// coalesce; a compact loop keeps the kernel inside the instruction cache).  Returns false when every
+// lane abandoned.
+template <int T>
+__device__ __forceinline__ bool score_pair(const uint32_t *__restrict__ rp, const ScanLayout &lay, const float *__restrict__ slut,
                                            const float *__restrict__ gspill, int t, float thr, bool active,
                                            float &dist_out) {
-  uint32_t wd[4 * W + 1];
+  float dist = 0.f;
+  const int M = lay.M;
+  for (int g = 0; g < M; g += 4) {
+    float dism = 0.f;
 #pragma unroll
-  for (int j = 0; j < W; j++) {
-    wd[4 * j + 0] = cw[j].x; wd[4 * j + 1] = cw[j].y; wd[4 * j + 2] = cw[j].z; wd[4 * j + 3] = cw[j].w;
-  }
-  wd[4 * W] = 0u;
-  float dist = 0.f, dism = 0.f;
-  int f = 0;
-#pragma unroll
-  for (int w = 0; w < 4 * W; w++) {
-    const int fe = lay.fbeg[w + 1];
-    const uint32_t lo = wd[w], hi = wd[w + 1];
-    for (; f < fe; f++) {
-      const uint32_t meta = lay.fmeta[f];
-      const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
-      const uint32_t idx = (lay.foff[f] + code) * T + t;
-      const float v = (meta & kFieldSpill) ? __ldg(gspill + idx) : slut[idx];
-      dism += v;
-      if ((f & 3) == 3) {
-        dist += dism;
-        dism = 0.f;
-        if (__all_sync(0xffffffffu, !active || (dist > thr))) return false;
+    for (int j = 0; j < 4; j++) {
+      const int f = g + j;
+      if (f < M) {
+        const uint32_t meta = lay.fmeta[f];
+        const uint32_t lo = __ldg(rp + lay.fw_lo[f]), hi = __ldg(rp + lay.fw_hi[f]);
+        const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
+        const uint32_t idx = (lay.foff[f] + code) * T + t;
+        const float v = (meta & kFieldSpill) ? __ldg(gspill + idx) : slut[idx];
+        dism += v;
       }
     }
+    dist += dism;
+    if (__all_sync(0xffffffffu, !active || (dist > thr))) return false;
   }
-  if (lay.M & 3) dist += dism;
   dist_out = dist;
   return true;
 }
 
 template <int W, int T>
-__global__ void __launch_bounds__(512, 1) adc_filter_scan_kernel(const __grid_constant__ AdcFilterArgs a) {
+__global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_constant__ AdcFilterArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int k = a.k;
   const int qt = blockIdx.x, chunk = blockIdx.y;
   const int q0 = qt * T;
+  constexpr int kQueueCap = 32 * (T + 1);      // 31 pending + one tile's pushes for T queries
 
   const size_t lut_bytes = (size_t)a.smem_lut_floats * T * sizeof(float);
   float *slut = reinterpret_cast<float *>(smem_raw);
-  uint32_t *thr_f = reinterpret_cast<uint32_t *>(smem_raw + ((lut_bytes + 15) & ~(size_t)15));   // [8] distance bits of blk_thr
-  uint64_t *lists = reinterpret_cast<uint64_t *>(thr_f + 8);                                   // [nwarps][T][k]
-  uint64_t *merged = lists + (size_t)nwarps * T * k;                                           // [k]
-  uint64_t *blk_thr = merged + k;                                                              // [T]
-  uint64_t *bar = blk_thr + T;
+  uint32_t *thr_f = reinterpret_cast<uint32_t *>(smem_raw + ((lut_bytes + 15) & ~(size_t)15));   // [8] k-th distance bits per query
+  uint32_t *locks = thr_f + 8;                                                                 // [8] per-query list locks
+  uint64_t *lists = reinterpret_cast<uint64_t *>(locks + 8);                                   // [T][k] ascending keys
+  uint64_t *bar = lists + (size_t)T * k;
   uint32_t *queues = reinterpret_cast<uint32_t *>(bar + 1);                                    // [nwarps][kQueueCap]
 
   const float *glut = a.lut + (size_t)qt * a.lut_stride * T;       // this tile's interleaved tables
   const float *gspill = glut + (size_t)a.smem_lut_floats * T;
 
-  for (int i = tid; i < nwarps * T * k; i += blockDim.x) lists[i] = kEmptyKey;
-  if (tid < T) {
-    const int q = min(q0 + tid, a.nq - 1);
-    const uint32_t g = a.thr_global[q];
-    blk_thr[tid] = ((uint64_t)g << 32) | 0xFFFFFFFFull;
-    thr_f[tid] = g;
+  for (int i = tid; i < T * k; i += blockDim.x) lists[i] = kEmptyKey;
+  if (tid < 8) {
+    const int q = min(q0 + min(tid, T - 1), a.nq - 1);
+    thr_f[tid] = a.thr_global[q];
+    locks[tid] = 0u;
   }
   if (lut_bytes) {
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -185,137 +179,117 @@ __global__ void __launch_bounds__(512, 1) adc_filter_scan_kernel(const __grid_co
   const int64_t n_tiles = (a.n_rows + kTileRows - 1) >> 5;
   const int64_t tile_end = min(n_tiles, tile_begin + a.chunk_tiles);
   const int64_t row_base = tile_begin << 5;
+  const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
 
-  // ---- stage 2 on up to 32 queued pairs -------------------------------------------------------
-  auto drain = [&](int take) {
-    const bool active = lane < take;
-    const uint32_t e = active ? myq[qn - take + lane] : 0u;
-    qn -= take;
-    const int t = (int)(e & 7u);
-    const int64_t row = row_base + (e >> 3);
-    uint4 cw[W];
-    {
-      const uint4 *p = a.codes + ((size_t)(row >> 5) * W) * kTileRows + (row & 31);
-#pragma unroll
-      for (int j = 0; j < W; j++) cw[j] = active ? __ldg(p + j * kTileRows) : make_uint4(0, 0, 0, 0);
-    }
-    volatile uint64_t *mylist = lists + ((size_t)warp * T + t) * k;
-    uint64_t thrkey = kEmptyKey;
-    if (active) {
-      thrkey = mylist[k - 1];
-      const uint64_t b = *reinterpret_cast<volatile uint64_t *>(blk_thr + t);
-      thrkey = b < thrkey ? b : thrkey;
-    }
-    const float thr = __uint_as_float((uint32_t)(thrkey >> 32));
-    float dist = 0.f;
-    if (!score_pair<W, T>(cw, a.lay, slut, gspill, t, thr, active, dist)) return;
-    const uint64_t key = active ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
-    unsigned m = __ballot_sync(0xffffffffu, key < thrkey);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
-      const int tt = __shfl_sync(0xffffffffu, t, src);
-      volatile uint64_t *lst = lists + ((size_t)warp * T + tt) * k;
-      const uint64_t before = lst[k - 1];
-      const uint64_t kth = warp_list_insert(lst, k, kk, lane);
-      if (lane == 0 && kth != before && kth != kEmptyKey) {
-        atomicMin(reinterpret_cast<unsigned long long *>(blk_thr + tt), (unsigned long long)kth);
-        atomicMin(thr_f + tt, (uint32_t)(kth >> 32));
-      }
-    }
-  };
+  int64_t tl = tile_begin + warp;
+  uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0, b2 = b0;
+  if (tl < tile_end) b0 = ldg_stream_u4(a.codes + ((size_t)tl * W) * kTileRows + lane);
+  if (tl + nwarps < tile_end) b1 = ldg_stream_u4(a.codes + ((size_t)(tl + nwarps) * W) * kTileRows + lane);
+  if (tl + 2 * nwarps < tile_end) b2 = ldg_stream_u4(a.codes + ((size_t)(tl + 2 * nwarps) * W) * kTileRows + lane);
+  int refresh = 0;
 
-  // ---- stage 1 --------------------------------------------------------------------------------
-  const int64_t t0 = tile_begin + warp;
-  uint4 buf[kPrefetch];
-#pragma unroll
-  for (int i = 0; i < kPrefetch; i++) {
-    const int64_t tl = t0 + (int64_t)i * nwarps;
-    buf[i] = make_uint4(0, 0, 0, 0);
-    if (tl < tile_end) buf[i] = ldg_stream_u4(a.codes + ((size_t)tl * W) * kTileRows + lane);
-  }
-  for (int64_t base = t0; base < tile_end; base += (int64_t)kPrefetch * nwarps) {
-#pragma unroll
-    for (int i = 0; i < kPrefetch; i++) {
-      const int64_t tl = base + (int64_t)i * nwarps;
-      if (tl >= tile_end) break;
-      const uint4 w0 = buf[i];
-      const int64_t tn = tl + (int64_t)kPrefetch * nwarps;
-      if (tn < tile_end) buf[i] = ldg_stream_u4(a.codes + ((size_t)tn * W) * kTileRows + lane);
-
-      // thresholds of the T queries (distance part of the block-wide k-th keys)
-      float thr[T];
-      lds_thr<T>(thr, thr_f);
-
-      float dism[T];
-#pragma unroll
-      for (int i1 = 0; i1 < 4; i1++) {
-        if (i1 < G1) {
-          const uint32_t lo = s1_hi[i1] ? w0.y : w0.x, hi = s1_hi[i1] ? w0.z : w0.y;
-          const uint32_t code = __funnelshift_r(lo, hi, s1_sh[i1]) & s1_mask[i1];
-          float v[T];
-          if (s1_spill[i1]) ldg_vec<T>(v, gspill + s1_off[i1] + code * T);
-          else lds_vec<T>(v, slut + s1_off[i1] + code * T);
-#pragma unroll
-          for (int t = 0; t < T; t++) dism[t] = (i1 == 0) ? v[t] : dism[t] + v[t];
-        }
-      }
-      const int64_t row = (tl << 5) + lane;
-      const bool valid = row < a.n_rows;
-      unsigned sb = 0;
-#pragma unroll
-      for (int t = 0; t < T; t++) sb |= (valid && !(dism[t] > thr[t]) && (q0 + t < a.nq)) ? (1u << t) : 0u;
-      if (__any_sync(0xffffffffu, sb != 0)) {
-        const uint32_t rel = (uint32_t)(row - row_base) << 3;
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-          const unsigned m = __ballot_sync(0xffffffffu, (sb >> t) & 1u);
-          if (m) {
-            if ((sb >> t) & 1u) myq[qn + __popc(m & lt_mask)] = rel | (uint32_t)t;
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) drain(32);
+  while (true) {
+    const bool more = tl < tile_end;
+    if (qn >= 32 || (!more && qn > 0)) {
+      // ---- stage 2 on up to 32 queued pairs (single code site) -----------------------------------
+      const int take = min(qn, 32);
+      const bool active = lane < take;
+      const uint32_t e = active ? myq[qn - take + lane] : 0u;
+      qn -= take;
+      const int t = (int)(e & 7u);
+      const int64_t row = row_base + (e >> 3);
+      const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
+      const float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
+      float dist = 0.f;
+      if (score_pair<T>(rp, a.lay, slut, gspill, t, thr, active, dist)) {
+        const uint64_t key = active ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
+        const uint64_t kth0 = active ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
+        unsigned m = __ballot_sync(0xffffffffu, key < kth0);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
+          const int tt = __shfl_sync(0xffffffffu, t, src);
+          volatile uint64_t *lst = lists + (size_t)tt * k;
+          if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) {}
+          __syncwarp();
+          const uint64_t before = lst[k - 1];
+          const uint64_t kth = warp_list_insert(lst, k, kk, lane);
+          __syncwarp();
+          if (lane == 0) {
+            if (kth != before && kth != kEmptyKey) {
+              const uint32_t bits = (uint32_t)(kth >> 32);
+              atomicMin(thr_f + tt, bits);
+              if (q0 + tt < a.nq) atomicMin(a.thr_global + q0 + tt, bits);
+            }
+            __threadfence_block();
+            atomicExch(locks + tt, 0u);
           }
         }
       }
+      continue;
     }
-  }
-  __syncwarp();
-  if (qn > 0) drain(qn);
+    if (!more) break;
 
-  // ---- CTA epilogue: merge the warps' lists per query, publish keys and the new bound -----------
-  __syncthreads();
-  for (int t = 0; t < T; t++) {
-    const int q = q0 + t;
-    if (q >= a.nq) break;
-    for (int i = tid; i < k; i += blockDim.x) merged[i] = kEmptyKey;
-    __syncthreads();
-    const int total = nwarps * k;
-    for (int e = tid; e < total; e += blockDim.x) {
-      const int l = e / k, i = e - l * k;
-      const uint64_t key = lists[((size_t)l * T + t) * k + i];
-      if (key == kEmptyKey) continue;
-      int rank = i;
-      for (int o = 0; o < nwarps && rank < k; o++) {
-        if (o == l) continue;
-        rank += lower_bound_u64(lists + ((size_t)o * T + t) * k, k, key);
-      }
-      if (rank < k) merged[rank] = key;
+    // ---- stage 1 on one tile ---------------------------------------------------------------------
+    const uint4 w0 = b0;
+    b0 = b1; b1 = b2;
+    {
+      const int64_t tn = tl + 3 * (int64_t)nwarps;
+      if (tn < tile_end) b2 = ldg_stream_u4(a.codes + ((size_t)tn * W) * kTileRows + lane);
     }
-    __syncthreads();
-    uint64_t *out = a.out_keys + ((size_t)q * a.n_chunks + chunk) * k;
-    for (int i = tid; i < k; i += blockDim.x) out[i] = merged[i];
-    if (tid == 0 && merged[k - 1] != kEmptyKey) atomicMin(a.thr_global + q, (uint32_t)(merged[k - 1] >> 32));
-    __syncthreads();
+    if (((++refresh) & 63) == 0 && lane < T && q0 + lane < a.nq) {
+      // pick up bounds published by other row chunks of this query tile
+      atomicMin(thr_f + lane, *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane));
+    }
+    float thr[T];
+    lds_thr<T>(thr, thr_f);
+
+    float dism[T];
+#pragma unroll
+    for (int i1 = 0; i1 < 4; i1++) {
+      if (i1 < G1) {
+        const uint32_t lo = s1_hi[i1] ? w0.y : w0.x, hi = s1_hi[i1] ? w0.z : w0.y;
+        const uint32_t code = __funnelshift_r(lo, hi, s1_sh[i1]) & s1_mask[i1];
+        float v[T];
+        if (s1_spill[i1]) ldg_vec<T>(v, gspill + s1_off[i1] + code * T);
+        else lds_vec<T>(v, slut + s1_off[i1] + code * T);
+#pragma unroll
+        for (int t = 0; t < T; t++) dism[t] = (i1 == 0) ? v[t] : dism[t] + v[t];
+      }
+    }
+    const int64_t row = (tl << 5) + lane;
+    const bool valid = row < a.n_rows;
+    unsigned sb = 0;
+#pragma unroll
+    for (int t = 0; t < T; t++) sb |= (valid && !(dism[t] > thr[t]) && (q0 + t < a.nq)) ? (1u << t) : 0u;
+    if (__any_sync(0xffffffffu, sb != 0)) {
+      const uint32_t rel = (uint32_t)(row - row_base) << 3;
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        const unsigned m = __ballot_sync(0xffffffffu, (sb >> t) & 1u);
+        if ((sb >> t) & 1u) myq[qn + __popc(m & lt_mask)] = rel | (uint32_t)t;
+        qn += __popc(m);
+      }
+      __syncwarp();
+    }
+    tl += nwarps;
+  }
+
+  // ---- CTA epilogue: publish this (query tile, chunk)'s keys -----------------------------------------
+  __syncthreads();
+  for (int i = tid; i < T * k; i += blockDim.x) {
+    const int t = i / k, j = i - t * k;
+    const int q = q0 + t;
+    if (q < a.nq) a.out_keys[((size_t)q * a.n_chunks + chunk) * k + j] = lists[i];
   }
 }
 
 size_t adc_filter_smem_bytes(int smem_lut_floats, int T, int k, int threads) {
   const int nwarps = threads / 32;
-  size_t b = (((size_t)smem_lut_floats * T * 4 + 15) & ~(size_t)15) + 32;
-  b += ((size_t)nwarps * T * k + k + T + 1) * sizeof(uint64_t);
-  b += (size_t)nwarps * kQueueCap * sizeof(uint32_t);
+  size_t b = (((size_t)smem_lut_floats * T * 4 + 15) & ~(size_t)15) + 64;
+  b += ((size_t)T * k + 1) * sizeof(uint64_t);
+  b += (size_t)nwarps * 32 * (T + 1) * sizeof(uint32_t);
   return b;
 }
 

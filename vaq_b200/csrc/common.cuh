@@ -24,6 +24,8 @@ struct ScanLayout {
   uint32_t fmeta[kMaxSubspaces];      // see above
   uint32_t foff[kMaxSubspaces];       // entry offset of table s inside the smem LUT or the spill area
   uint8_t fword[kMaxSubspaces];       // 32-bit word in which field s starts
+  uint16_t fw_lo[kMaxSubspaces];      // offset (32-bit units, from the row's first word in the tiled layout) of that
+  uint16_t fw_hi[kMaxSubspaces];      //   word and of the following one (== fw_lo when the row ends there)
 };
 
 // Where the LUT build kernel writes table s inside a query's LUT row.

@@ -194,7 +194,12 @@ int plan_model(vaqgpu_index *h) {
   }
   lay.fbeg[4 * W] = (uint16_t)M;
 
-  for (int s = 0; s < M; s++) lay.fword[s] = (uint8_t)word_of[s];
+  for (int s = 0; s < M; s++) {
+    lay.fword[s] = (uint8_t)word_of[s];
+    auto woff = [](int w) { return (uint16_t)((w >> 2) * kTileRows * 4 + (w & 3)); };   // tiled layout: uint4 j of a row is 32 uint4 apart
+    lay.fw_lo[s] = woff(word_of[s]);
+    lay.fw_hi[s] = word_of[s] + 1 < 4 * W ? woff(word_of[s] + 1) : lay.fw_lo[s];
+  }
   plan.T = 1;
   return VAQGPU_OK;
 }
@@ -288,21 +293,18 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
 
   if (filter) {
     // ---- query-tile width T and residency -------------------------------------------------------
-    int threads = 512;
+    const int threads = 1024;
     int T = nq >= 8 ? 8 : (nq >= 3 ? 4 : nq);
     for (;; T >>= 1) {
       const size_t fixed = adc_filter_smem_bytes(0, T, k, threads) + 1024;
-      if (fixed < kSmemCap) {
-        const size_t budget = (kSmemCap - fixed) / (4 * (size_t)T);
-        if ((size_t)h->total_entries + 4 <= budget || T == 1) {
-          apply_residency(h, budget, T, lay, plan, res_floats, spill_floats);
-          break;
-        }
+      if (fixed >= kSmemCap) {
+        if (T == 1) return fail(VAQGPU_EINVAL, "k=%d does not fit the scan's shared memory", k);
+        continue;
       }
-      if (T == 1) {
-        threads >>= 1;
-        if (threads < 64) return fail(VAQGPU_EINVAL, "k=%d does not fit the scan's shared memory", k);
-        T = 2;   // retry T=1 with fewer warps (fewer per-warp lists)
+      const size_t budget = (kSmemCap - fixed) / (4 * (size_t)T);
+      if ((size_t)h->total_entries + 4 <= budget || T == 1) {     // T > 1 only with every table resident
+        apply_residency(h, budget, T, lay, plan, res_floats, spill_floats);
+        break;
       }
     }
     const size_t smem = adc_filter_smem_bytes(res_floats, T, k, threads);
