@@ -175,17 +175,17 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   int qn = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  const int64_t tile_begin = (int64_t)chunk * a.chunk_tiles;
-  const int64_t n_tiles = (a.n_rows + kTileRows - 1) >> 5;
-  const int64_t tile_end = min(n_tiles, tile_begin + a.chunk_tiles);
+  const int64_t tile_begin = a.tile_lo + (int64_t)chunk * a.chunk_tiles;
+  const int64_t tile_end = min(a.tile_hi, tile_begin + a.chunk_tiles);
   const int64_t row_base = tile_begin << 5;
   const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
 
   int64_t tl = tile_begin + warp;
-  uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0, b2 = b0;
+  uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0, b2 = b0, b3 = b0;
   if (tl < tile_end) b0 = ldg_stream_u4(a.codes + ((size_t)tl * W) * kTileRows + lane);
   if (tl + nwarps < tile_end) b1 = ldg_stream_u4(a.codes + ((size_t)(tl + nwarps) * W) * kTileRows + lane);
   if (tl + 2 * nwarps < tile_end) b2 = ldg_stream_u4(a.codes + ((size_t)(tl + 2 * nwarps) * W) * kTileRows + lane);
+  if (tl + 3 * nwarps < tile_end) b3 = ldg_stream_u4(a.codes + ((size_t)(tl + 3 * nwarps) * W) * kTileRows + lane);
   int refresh = 0;
 
   while (true) {
@@ -211,19 +211,25 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
           const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
           const int tt = __shfl_sync(0xffffffffu, t, src);
           volatile uint64_t *lst = lists + (size_t)tt * k;
-          if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) {}
+          // other warps tighten the list all the time: re-check before paying for the lock
+          {
+            uint64_t cur = lst[k - 1];
+            cur = __shfl_sync(0xffffffffu, cur, 0);      // one observer: the decision must be warp-uniform
+            if (!(kk < cur)) continue;
+          }
+          if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) __nanosleep(20);
           __syncwarp();
           const uint64_t before = lst[k - 1];
           const uint64_t kth = warp_list_insert(lst, k, kk, lane);
           __syncwarp();
           if (lane == 0) {
+            __threadfence_block();
+            atomicExch(locks + tt, 0u);
             if (kth != before && kth != kEmptyKey) {
               const uint32_t bits = (uint32_t)(kth >> 32);
               atomicMin(thr_f + tt, bits);
               if (q0 + tt < a.nq) atomicMin(a.thr_global + q0 + tt, bits);
             }
-            __threadfence_block();
-            atomicExch(locks + tt, 0u);
           }
         }
       }
@@ -233,10 +239,10 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
 
     // ---- stage 1 on one tile ---------------------------------------------------------------------
     const uint4 w0 = b0;
-    b0 = b1; b1 = b2;
+    b0 = b1; b1 = b2; b2 = b3;
     {
-      const int64_t tn = tl + 3 * (int64_t)nwarps;
-      if (tn < tile_end) b2 = ldg_stream_u4(a.codes + ((size_t)tn * W) * kTileRows + lane);
+      const int64_t tn = tl + 4 * (int64_t)nwarps;
+      if (tn < tile_end) b3 = ldg_stream_u4(a.codes + ((size_t)tn * W) * kTileRows + lane);
     }
     if (((++refresh) & 63) == 0 && lane < T && q0 + lane < a.nq) {
       // pick up bounds published by other row chunks of this query tile
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   for (int i = tid; i < T * k; i += blockDim.x) {
     const int t = i / k, j = i - t * k;
     const int q = q0 + t;
-    if (q < a.nq) a.out_keys[((size_t)q * a.n_chunks + chunk) * k + j] = lists[i];
+    if (q < a.nq) a.out_keys[((size_t)q * a.out_slots + a.slot_base + chunk) * k + j] = lists[i];
   }
 }
 
@@ -301,7 +307,9 @@ static cudaError_t launch_wt(const AdcFilterArgs &a, int threads, size_t smem_by
     if (e != cudaSuccess) return e;
     configured = smem_bytes;
   }
-  dim3 grid((unsigned)((a.nq + T - 1) / T), (unsigned)a.n_chunks);
+  const int64_t nt = a.tile_hi - a.tile_lo;
+  if (nt <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((a.nq + T - 1) / T), (unsigned)((nt + a.chunk_tiles - 1) / a.chunk_tiles));
   adc_filter_scan_kernel<W, T><<<grid, threads, smem_bytes, st>>>(a);
   return cudaGetLastError();
 }

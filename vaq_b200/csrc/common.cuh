@@ -179,9 +179,11 @@ struct AdcFilterArgs {
   int32_t lut_stride;        // entries per query (row_stride)
   int32_t smem_lut_floats;   // resident entries per query (multiple of 4)
   int32_t nq, k;
-  int32_t chunk_tiles;       // 32-row tiles per row chunk
-  int32_t n_chunks;
-  uint64_t *out_keys;        // [nq][n_chunks][k]; low word = LOCAL row index
+  int64_t tile_lo, tile_hi;  // 32-row tiles scanned by this launch
+  int32_t chunk_tiles;       // tiles per row chunk (grid.y = ceil((tile_hi - tile_lo) / chunk_tiles))
+  int32_t out_slots;         // key lists per query in out_keys (over all launches of the search)
+  int32_t slot_base;         // this launch's first list
+  uint64_t *out_keys;        // [nq][out_slots][k]; low word = LOCAL row index
   uint32_t *thr_global;      // [nq] float bits of the best known k-th distance (0xFFFFFFFF = none)
   ScanLayout lay;
 };

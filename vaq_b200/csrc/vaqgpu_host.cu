@@ -324,10 +324,25 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     if (n_chunks > 65535) return fail(VAQGPU_EINVAL, "index too large for one launch (%lld chunks)", (long long)n_chunks);
 
+    // Warm-up passes: scanning a short row prefix first gives every query a usable k-th-best bound
+    // before the main pass starts (a CTA that starts with no bound has to score everything it sees).
+    // Prefixes of 2K and 32K rows, only when the index is much larger than that.
+    int64_t warm[2] = {0, 0};
+    int n_warm = 0;
+    if (n_tiles >= 64 * 16) warm[n_warm++] = 64;
+    if (n_tiles >= 1024 * 16) warm[n_warm++] = 1024;
+    const int64_t main_lo = n_warm ? warm[n_warm - 1] : 0;
+    {
+      const int64_t main_tiles = n_tiles - main_lo;
+      chunk_tiles = (main_tiles + n_chunks - 1) / n_chunks;
+      n_chunks = (main_tiles + chunk_tiles - 1) / chunk_tiles;
+    }
+    const int out_slots = (int)n_chunks + n_warm;
+
     CU(h->w_lut.ensure((size_t)qb_max * bytes_per_q));
-    CU(h->w_keys.ensure((size_t)qb_max * n_chunks * k * sizeof(uint64_t)));
+    CU(h->w_keys.ensure((size_t)qb_max * out_slots * k * sizeof(uint64_t)));
     CU(h->w_thr.ensure((size_t)qb_max * sizeof(uint32_t)));
-    if (n_chunks > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((n_chunks + 15) / 16) * k * sizeof(uint64_t)));
+    if (out_slots > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((out_slots + 15) / 16) * k * sizeof(uint64_t)));
 
     for (int q0 = 0; q0 < nq; q0 += qb_max) {
       const int qb = std::min(qb_max, nq - q0);
@@ -340,22 +355,30 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       AdcFilterArgs a{};
       a.codes = h->d_codes; a.n_rows = h->n_rows;
       a.lut = (const float *)h->w_lut.p; a.lut_stride = plan.row_stride; a.smem_lut_floats = res_floats;
-      a.nq = qb; a.k = k; a.chunk_tiles = (int32_t)chunk_tiles; a.n_chunks = (int32_t)n_chunks;
+      a.nq = qb; a.k = k; a.out_slots = out_slots;
       a.out_keys = (uint64_t *)h->w_keys.p;
       a.thr_global = (uint32_t *)h->w_thr.p;
       a.lay = lay;
+      int64_t lo = 0;
+      for (int wi = 0; wi < n_warm; wi++) {
+        a.tile_lo = lo; a.tile_hi = warm[wi]; a.chunk_tiles = (int32_t)(warm[wi] - lo); a.slot_base = wi;
+        CU(launch_adc_filter_scan(a, T, threads, smem, st));
+        launches++;
+        lo = warm[wi];
+      }
+      a.tile_lo = main_lo; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles; a.slot_base = n_warm;
       CU(launch_adc_filter_scan(a, T, threads, smem, st));
       launches++;
       if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
-      CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)n_chunks * k, (int)n_chunks, qb, k, want_sqrt ? 1 : 0, 0,
+      CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)out_slots * k, out_slots, qb, k, want_sqrt ? 1 : 0, 0,
                            d_labels ? d_labels + (size_t)q0 * k : nullptr, d_dists ? (void *)(d_dists + (size_t)q0 * k) : nullptr,
                            d_keys ? d_keys + (size_t)q0 * k : nullptr, nullptr, h->id_base, (uint64_t *)h->w_scratch.p, st));
-      launches += n_chunks > 16 ? 2 : 1;
+      launches += out_slots > 16 ? 2 : 1;
     }
     if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
     h->cfg[0] = threads; h->cfg[1] = (int32_t)n_chunks; h->cfg[2] = res_floats; h->cfg[3] = spill_floats;
     h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
-    h->cfg[8] = T; h->cfg[9] = 2;
+    h->cfg[8] = T; h->cfg[9] = 2; h->cfg[10] = n_warm;
     return VAQGPU_OK;
   }
 
