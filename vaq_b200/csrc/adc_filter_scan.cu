@@ -83,23 +83,21 @@ __device__ __forceinline__ void lds_thr(float (&out)[T], const uint32_t *p) {
   }
 }
 
-// Full-precision score of one (row, query) pair per lane, all subspaces in the reference's order and
-// grouping (dism = ((l0+l1)+l2)+l3 ; dist += dism, VAQ.cpp:1741-1748).  The row's 32-bit words are
-// fetched through L1 as the walk needs them (each lane has a different row, so there is nothing to
-// coalesce; a compact loop keeps the kernel inside the instruction cache).  Returns false when every
-// lane abandoned.
+// Exact score of one (row, query) pair per lane over the fields [f_begin, f_end) (f_begin a multiple of
+// 4), continuing from `dist`, in the reference's order and grouping (dism = ((l0+l1)+l2)+l3 ;
+// dist += dism, VAQ.cpp:1741-1748).  The row's 32-bit words are fetched through L1 as the walk needs
+// them (each lane has a different row, so there is nothing to coalesce; a compact loop keeps the kernel
+// inside the instruction cache).  Returns false when every lane abandoned.
 template <int T>
-__device__ __forceinline__ bool score_pair(const uint32_t *__restrict__ rp, const ScanLayout &lay, const float *__restrict__ slut,
-                                           const float *__restrict__ gspill, int t, float thr, bool active,
-                                           float &dist_out) {
-  float dist = 0.f;
-  const int M = lay.M;
-  for (int g = 0; g < M; g += 4) {
+__device__ __forceinline__ bool score_fields(const uint32_t *__restrict__ rp, const ScanLayout &lay, const float *__restrict__ slut,
+                                             const float *__restrict__ gspill, int t, float thr, bool active, int f_begin,
+                                             int f_end, float &dist) {
+  for (int g = f_begin; g < f_end; g += 4) {
     float dism = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int f = g + j;
-      if (f < M) {
+      if (f < f_end) {
         const uint32_t meta = lay.fmeta[f];
         const uint32_t lo = __ldg(rp + lay.fw_lo[f]), hi = __ldg(rp + lay.fw_hi[f]);
         const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
@@ -111,9 +109,10 @@ __device__ __forceinline__ bool score_pair(const uint32_t *__restrict__ rp, cons
     dist += dism;
     if (__all_sync(0xffffffffu, !active || (dist > thr))) return false;
   }
-  dist_out = dist;
   return true;
 }
+
+constexpr int kQ2Cap = 64;                                         // 31 pending + one level-1 drain
 
 template <int W, int T>
 __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_constant__ AdcFilterArgs a) {
@@ -122,7 +121,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   const int k = a.k;
   const int qt = blockIdx.x, chunk = blockIdx.y;
   const int q0 = qt * T;
-  constexpr int kQueueCap = 32 * (T + 1);      // 31 pending + one tile's pushes for T queries
+  constexpr int kQ1Cap = 32 + 64 * T;             // 31 pending + two tiles' pushes for T queries
 
   const size_t lut_bytes = (size_t)a.smem_lut_floats * T * sizeof(float);
   float *slut = reinterpret_cast<float *>(smem_raw);
@@ -130,7 +129,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   uint32_t *locks = thr_f + 8;                                                                 // [8] per-query list locks
   uint64_t *lists = reinterpret_cast<uint64_t *>(locks + 8);                                   // [T][k] ascending keys
   uint64_t *bar = lists + (size_t)T * k;
-  uint32_t *queues = reinterpret_cast<uint32_t *>(bar + 1);                                    // [nwarps][kQueueCap]
+  uint32_t *queues = reinterpret_cast<uint32_t *>(bar + 1);                                    // per warp: q1 | q2 entries | q2 dists
 
   const float *glut = a.lut + (size_t)qt * a.lut_stride * T;       // this tile's interleaved tables
   const float *gspill = glut + (size_t)a.smem_lut_floats * T;
@@ -157,7 +156,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   }
 
   // stage-1 program: the first group (<= 4 fields, <= 60 bits, i.e. inside 32-bit words 0..2)
-  const int G1 = min(4, a.lay.M);
+  const int M = a.lay.M;
+  const int G1 = min(4, M);
   uint32_t s1_sh[4], s1_mask[4], s1_off[4];
   bool s1_hi[4], s1_spill[4];
 #pragma unroll
@@ -170,9 +170,15 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
     s1_hi[i] = a.lay.fword[f] != 0;
     s1_spill[i] = (meta & kFieldSpill) != 0;
   }
+  // stage 2 runs in two levels when there are more than two groups: level 1 re-scores groups 1-2 exactly
+  // and keeps the pairs still under the bound, level 2 finishes them
+  const bool two_level = M > 8;
+  const int F2 = two_level ? 8 : M;
 
-  uint32_t *myq = queues + warp * kQueueCap;
-  int qn = 0;
+  uint32_t *q1 = queues + (size_t)warp * (kQ1Cap + 2 * kQ2Cap);
+  uint32_t *q2e = q1 + kQ1Cap;
+  float *q2d = reinterpret_cast<float *>(q2e + kQ2Cap);
+  int q1n = 0, q2n = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   const int64_t tile_begin = a.tile_lo + (int64_t)chunk * a.chunk_tiles;
@@ -180,77 +186,15 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   const int64_t row_base = tile_begin << 5;
   const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
 
-  int64_t tl = tile_begin + warp;
-  uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0, b2 = b0, b3 = b0;
-  if (tl < tile_end) b0 = ldg_stream_u4(a.codes + ((size_t)tl * W) * kTileRows + lane);
-  if (tl + nwarps < tile_end) b1 = ldg_stream_u4(a.codes + ((size_t)(tl + nwarps) * W) * kTileRows + lane);
-  if (tl + 2 * nwarps < tile_end) b2 = ldg_stream_u4(a.codes + ((size_t)(tl + 2 * nwarps) * W) * kTileRows + lane);
-  if (tl + 3 * nwarps < tile_end) b3 = ldg_stream_u4(a.codes + ((size_t)(tl + 3 * nwarps) * W) * kTileRows + lane);
-  int refresh = 0;
-
-  while (true) {
-    const bool more = tl < tile_end;
-    if (qn >= 32 || (!more && qn > 0)) {
-      // ---- stage 2 on up to 32 queued pairs (single code site) -----------------------------------
-      const int take = min(qn, 32);
-      const bool active = lane < take;
-      const uint32_t e = active ? myq[qn - take + lane] : 0u;
-      qn -= take;
-      const int t = (int)(e & 7u);
-      const int64_t row = row_base + (e >> 3);
-      const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
-      const float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
-      float dist = 0.f;
-      if (score_pair<T>(rp, a.lay, slut, gspill, t, thr, active, dist)) {
-        const uint64_t key = active ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
-        const uint64_t kth0 = active ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
-        unsigned m = __ballot_sync(0xffffffffu, key < kth0);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
-          const int tt = __shfl_sync(0xffffffffu, t, src);
-          volatile uint64_t *lst = lists + (size_t)tt * k;
-          // other warps tighten the list all the time: re-check before paying for the lock
-          {
-            uint64_t cur = lst[k - 1];
-            cur = __shfl_sync(0xffffffffu, cur, 0);      // one observer: the decision must be warp-uniform
-            if (!(kk < cur)) continue;
-          }
-          if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) __nanosleep(20);
-          __syncwarp();
-          const uint64_t before = lst[k - 1];
-          const uint64_t kth = warp_list_insert(lst, k, kk, lane);
-          __syncwarp();
-          if (lane == 0) {
-            __threadfence_block();
-            atomicExch(locks + tt, 0u);
-            if (kth != before && kth != kEmptyKey) {
-              const uint32_t bits = (uint32_t)(kth >> 32);
-              atomicMin(thr_f + tt, bits);
-              if (q0 + tt < a.nq) atomicMin(a.thr_global + q0 + tt, bits);
-            }
-          }
-        }
-      }
-      continue;
-    }
-    if (!more) break;
-
-    // ---- stage 1 on one tile ---------------------------------------------------------------------
-    const uint4 w0 = b0;
-    b0 = b1; b1 = b2; b2 = b3;
+  // stage 1 on one tile whose first words are in `buf`; refills `buf` with the tile 2*nwarps further on
+  auto stage1 = [&](uint4 &buf, int64_t tile) {
+    const uint4 w0 = buf;
     {
-      const int64_t tn = tl + 4 * (int64_t)nwarps;
-      if (tn < tile_end) b3 = ldg_stream_u4(a.codes + ((size_t)tn * W) * kTileRows + lane);
-    }
-    if (((++refresh) & 63) == 0 && lane < T && q0 + lane < a.nq) {
-      // pick up bounds published by other row chunks of this query tile
-      atomicMin(thr_f + lane, *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane));
+      const int64_t tn = tile + 2 * (int64_t)nwarps;
+      if (tn < tile_end) buf = ldg_stream_u4(a.codes + ((size_t)tn * W) * kTileRows + lane);
     }
     float thr[T];
     lds_thr<T>(thr, thr_f);
-
     float dism[T];
 #pragma unroll
     for (int i1 = 0; i1 < 4; i1++) {
@@ -264,7 +208,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
         for (int t = 0; t < T; t++) dism[t] = (i1 == 0) ? v[t] : dism[t] + v[t];
       }
     }
-    const int64_t row = (tl << 5) + lane;
+    const int64_t row = (tile << 5) + lane;
     const bool valid = row < a.n_rows;
     unsigned sb = 0;
 #pragma unroll
@@ -274,12 +218,100 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
 #pragma unroll
       for (int t = 0; t < T; t++) {
         const unsigned m = __ballot_sync(0xffffffffu, (sb >> t) & 1u);
-        if ((sb >> t) & 1u) myq[qn + __popc(m & lt_mask)] = rel | (uint32_t)t;
-        qn += __popc(m);
+        if ((sb >> t) & 1u) q1[q1n + __popc(m & lt_mask)] = rel | (uint32_t)t;
+        q1n += __popc(m);
       }
-      __syncwarp();
     }
-    tl += nwarps;
+  };
+
+  int64_t tl = tile_begin + warp;
+  uint4 bA = make_uint4(0, 0, 0, 0), bB = bA;
+  if (tl < tile_end) bA = ldg_stream_u4(a.codes + ((size_t)tl * W) * kTileRows + lane);
+  if (tl + nwarps < tile_end) bB = ldg_stream_u4(a.codes + ((size_t)(tl + nwarps) * W) * kTileRows + lane);
+  int refresh = 0;
+
+  while (true) {
+    const bool more = tl < tile_end;
+    int level = 0, take = 0;
+    if (q2n >= 32) { level = 2; take = 32; }
+    else if (q1n >= 32) { level = 1; take = 32; }
+    else if (!more) {
+      if (q1n > 0) { level = 1; take = q1n; }
+      else if (q2n > 0) { level = 2; take = q2n; }
+      else break;
+    }
+    if (level) {
+      // ---- stage 2 on up to 32 queued pairs (single code site for both levels) -----------------------
+      __syncwarp();
+      const bool active = lane < take;
+      uint32_t e = 0u;
+      float dist = 0.f;
+      int fb = 0, fe = F2;
+      if (level == 1) {
+        if (active) e = q1[q1n - take + lane];
+        q1n -= take;
+      } else {
+        if (active) { e = q2e[q2n - take + lane]; dist = q2d[q2n - take + lane]; }
+        q2n -= take;
+        fb = F2; fe = M;
+      }
+      const int t = (int)(e & 7u);
+      const int64_t row = row_base + (e >> 3);
+      const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
+      const float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
+      if (score_fields<T>(rp, a.lay, slut, gspill, t, thr, active, fb, fe, dist)) {
+        if (level == 1 && two_level) {
+          const bool s = active && !(dist > thr);
+          const unsigned m = __ballot_sync(0xffffffffu, s);
+          if (s) {
+            const int pos = q2n + __popc(m & lt_mask);
+            q2e[pos] = e;
+            q2d[pos] = dist;
+          }
+          q2n += __popc(m);
+        } else {
+          const uint64_t key = active ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
+          const uint64_t kth0 = active ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
+          unsigned m = __ballot_sync(0xffffffffu, key < kth0);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
+            const int tt = __shfl_sync(0xffffffffu, t, src);
+            volatile uint64_t *lst = lists + (size_t)tt * k;
+            {
+              uint64_t cur = lst[k - 1];
+              cur = __shfl_sync(0xffffffffu, cur, 0);      // one observer: the decision must be warp-uniform
+              if (!(kk < cur)) continue;
+            }
+            if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) __nanosleep(20);
+            __syncwarp();
+            const uint64_t before = lst[k - 1];
+            const uint64_t kth = warp_list_insert(lst, k, kk, lane);
+            __syncwarp();
+            if (lane == 0) {
+              __threadfence_block();
+              atomicExch(locks + tt, 0u);
+              if (kth != before && kth != kEmptyKey) {
+                const uint32_t bits = (uint32_t)(kth >> 32);
+                atomicMin(thr_f + tt, bits);
+                if (q0 + tt < a.nq) atomicMin(a.thr_global + q0 + tt, bits);
+              }
+            }
+          }
+        }
+      }
+      continue;
+    }
+
+    // ---- stage 1 on two tiles (two register buffers -> loads stay two iterations ahead) ---------------
+    if (((++refresh) & 31) == 0 && lane < T && q0 + lane < a.nq) {
+      // pick up bounds published by other row chunks of this query tile
+      atomicMin(thr_f + lane, *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane));
+    }
+    stage1(bA, tl);
+    if (tl + nwarps < tile_end) stage1(bB, tl + nwarps);
+    tl += 2 * (int64_t)nwarps;
   }
 
   // ---- CTA epilogue: publish this (query tile, chunk)'s keys -----------------------------------------
@@ -291,11 +323,82 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   }
 }
 
+// ---- bound seeding ------------------------------------------------------------------------------------
+// One CTA per query: scores kSample rows spread evenly over the index exactly (same summation order as
+// the scan), sorts the distances and publishes the k-th smallest as the query's initial bound.  Any k
+// rows give a valid bound (the true k-th best can only be smaller), so the scan that follows can prune
+// from its first tile instead of scoring everything until its own lists fill.
+constexpr int kSample = 4096;
+
+__global__ void __launch_bounds__(1024) adc_seed_bounds_kernel(const __grid_constant__ AdcSeedArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *vals = reinterpret_cast<uint32_t *>(smem_raw);                 // [kSample]
+  float *slut = reinterpret_cast<float *>(vals + kSample);                 // [lut_stride] this query's tables
+  const int q = blockIdx.x, T = a.T;
+  const float *glut = a.lut + (size_t)(q / T) * a.lut_stride * T + (q % T);
+  for (int i = threadIdx.x; i < a.lut_stride; i += blockDim.x) slut[i] = __ldg(glut + (size_t)i * T);
+  __syncthreads();
+  const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
+  const int W = a.lay.W, M = a.lay.M;
+  const int64_t step = a.n_rows / kSample;
+  for (int i = threadIdx.x; i < kSample; i += blockDim.x) {
+    const int64_t row = (int64_t)i * step;
+    const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
+    float dist = 0.f;
+    for (int g = 0; g < M; g += 4) {
+      float dism = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int f = g + j;
+        if (f < M) {
+          const uint32_t meta = a.lay.fmeta[f];
+          const uint32_t lo = __ldg(rp + a.lay.fw_lo[f]), hi = __ldg(rp + a.lay.fw_hi[f]);
+          const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
+          const uint32_t base = (meta & kFieldSpill) ? (uint32_t)a.smem_lut_floats : 0u;
+          dism += slut[base + a.lay.foff[f] + code];
+        }
+      }
+      dist += dism;
+    }
+    vals[i] = __float_as_uint(dist);
+  }
+  __syncthreads();
+  // bitonic sort, ascending (distances are non-negative: the bit patterns order like the floats)
+  for (int size = 2; size <= kSample; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < kSample / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const uint32_t x = vals[lo], y = vals[hi];
+        if ((x > y) == up) { vals[lo] = y; vals[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) atomicMin(a.thr_global + q, vals[a.k - 1]);
+}
+
+int adc_seed_sample_rows() { return kSample; }
+
+cudaError_t launch_adc_seed_bounds(const AdcSeedArgs &a, cudaStream_t st) {
+  if (a.nq <= 0) return cudaSuccess;
+  const size_t smem = (size_t)kSample * 4 + (size_t)a.lut_stride * 4;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(adc_seed_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  adc_seed_bounds_kernel<<<a.nq, 1024, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 size_t adc_filter_smem_bytes(int smem_lut_floats, int T, int k, int threads) {
   const int nwarps = threads / 32;
   size_t b = (((size_t)smem_lut_floats * T * 4 + 15) & ~(size_t)15) + 64;
   b += ((size_t)T * k + 1) * sizeof(uint64_t);
-  b += (size_t)nwarps * 32 * (T + 1) * sizeof(uint32_t);
+  b += (size_t)nwarps * (32 + 64 * T + 2 * kQ2Cap) * sizeof(uint32_t);
   return b;
 }
 

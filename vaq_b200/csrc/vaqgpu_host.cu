@@ -324,19 +324,12 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     if (n_chunks > 65535) return fail(VAQGPU_EINVAL, "index too large for one launch (%lld chunks)", (long long)n_chunks);
 
-    // Warm-up passes: scanning a short row prefix first gives every query a usable k-th-best bound
-    // before the main pass starts (a CTA that starts with no bound has to score everything it sees).
-    // Prefixes of 2K and 32K rows, only when the index is much larger than that.
-    int64_t warm[2] = {0, 0};
-    int n_warm = 0;
-    if (n_tiles >= 64 * 16) warm[n_warm++] = 64;
-    if (n_tiles >= 1024 * 16) warm[n_warm++] = 1024;
-    const int64_t main_lo = n_warm ? warm[n_warm - 1] : 0;
-    {
-      const int64_t main_tiles = n_tiles - main_lo;
-      chunk_tiles = (main_tiles + n_chunks - 1) / n_chunks;
-      n_chunks = (main_tiles + chunk_tiles - 1) / chunk_tiles;
-    }
+    // Bound seeding: a CTA that starts with no k-th-best bound has to score everything it sees, so a
+    // small kernel first scores a fixed sample of rows per query and publishes the k-th smallest.
+    const int sample = adc_seed_sample_rows();
+    const bool seed = h->n_rows >= 8 * (int64_t)sample && k <= sample / 4 &&
+                      (size_t)sample * 4 + (size_t)plan.row_stride * 4 <= kSmemCap;
+    const int n_warm = 0;
     const int out_slots = (int)n_chunks + n_warm;
 
     CU(h->w_lut.ensure((size_t)qb_max * bytes_per_q));
@@ -359,14 +352,15 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.out_keys = (uint64_t *)h->w_keys.p;
       a.thr_global = (uint32_t *)h->w_thr.p;
       a.lay = lay;
-      int64_t lo = 0;
-      for (int wi = 0; wi < n_warm; wi++) {
-        a.tile_lo = lo; a.tile_hi = warm[wi]; a.chunk_tiles = (int32_t)(warm[wi] - lo); a.slot_base = wi;
-        CU(launch_adc_filter_scan(a, T, threads, smem, st));
+      if (seed) {
+        AdcSeedArgs sa{};
+        sa.codes = h->d_codes; sa.n_rows = h->n_rows; sa.lut = (const float *)h->w_lut.p;
+        sa.lut_stride = plan.row_stride; sa.smem_lut_floats = res_floats; sa.T = T; sa.nq = qb; sa.k = k;
+        sa.thr_global = (uint32_t *)h->w_thr.p; sa.lay = lay;
+        CU(launch_adc_seed_bounds(sa, st));
         launches++;
-        lo = warm[wi];
       }
-      a.tile_lo = main_lo; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles; a.slot_base = n_warm;
+      a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles; a.slot_base = n_warm;
       CU(launch_adc_filter_scan(a, T, threads, smem, st));
       launches++;
       if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
@@ -378,7 +372,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
     h->cfg[0] = threads; h->cfg[1] = (int32_t)n_chunks; h->cfg[2] = res_floats; h->cfg[3] = spill_floats;
     h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
-    h->cfg[8] = T; h->cfg[9] = 2; h->cfg[10] = n_warm;
+    h->cfg[8] = T; h->cfg[9] = 2; h->cfg[10] = seed ? sample : 0;
     return VAQGPU_OK;
   }
 
