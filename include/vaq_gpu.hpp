@@ -1,0 +1,214 @@
+// vaq_gpu.hpp — header-only C++ host shim over the C ABI (vaqgpu.h) that mirrors the public surface of
+// the reference's two index classes for the query-time path:
+//
+//   class VAQ           bitvecengine/VAQ.hpp:36-114   (parseMethodString, encode, search, refine, mVisit ...)
+//   class BitVecEngine  bitvecengine/BitVecEngine.hpp:86-106, 1026, 1121, 1218  (loadBitV, appendBitV, query, queryParallel)
+//
+// Same names, argument meaning and result types (LabelDistVecF, IdxDistPair: utils/Types.hpp:42-51,
+// 98-104), so a caller such as examples/demo_vaq.cpp:339-345 keeps its code and only changes the type
+// it instantiates.  Training stays on the host in the reference (VAQ::train); a trained reference `VAQ`
+// hands its public members to loadModel().  Matrices are passed as row-major float pointers — exactly
+// RowMatrixXf::data() (utils/Types.hpp:14-18) — so the shim itself does not need Eigen.
+//
+// Error behaviour: the reference prints and calls exit(0)/assert(false) (VAQ.cpp:64-78, 1263-1266); the
+// shim throws std::runtime_error carrying vaqgpu_last_error().  There is no CPU fallback.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vaqgpu.h"
+
+namespace vaqgpu {
+
+// utils/Types.hpp:98-104
+struct LabelDistVecF {
+  std::vector<int> labels;
+  std::vector<float> distances;
+};
+// utils/Types.hpp:42-51
+struct IdxDistPair {
+  int idx;
+  uint32_t dist;
+};
+using bitv = std::vector<uint64_t>;        // BitVector.hpp:13
+using bitvectors = std::vector<bitv>;      // BitVector.hpp:19
+
+inline void check(int rc) {
+  if (rc != VAQGPU_OK) throw std::runtime_error(std::string("vaqgpu: ") + vaqgpu_last_error());
+}
+
+class VAQ {
+ public:
+  // VAQ::NNMethod, VAQ.hpp:38-49 (only the exact modes are implemented on the device; FAST* quantise the
+  // LUT to uint8 and SORT/FAST2/FAST3 write their results through a defective helper)
+  enum NNMethod { Sort = 1 << 0, EA = 1 << 1, TI = 1 << 2, Heap = 1 << 7 };
+
+  // knobs with the reference's names (VAQ.hpp:51-55, 84)
+  int mBitBudget = 0, mSubspaceNum = 0, mMinBitsPerSubs = 0, mMaxBitsPerSubs = 0;
+  float mPercentVarExplained = 1.f;
+  int mMethods = Heap;
+  float mVisit = 1.f;
+  int mTIClusterNum = 0;
+  int mSubsLen = 0, mHighestSubs = 0;
+
+  explicit VAQ(int device = 0) : device_(device) {}
+  ~VAQ() { vaqgpu_destroy(h_); }
+  VAQ(const VAQ &) = delete;
+  VAQ &operator=(const VAQ &) = delete;
+
+  // VAQ::parseMethodString, VAQ.cpp:1189-1267: "VAQ<budget>m<M>min<a>max<b>var<v>,<MODE>[_TI<c>]"
+  void parseMethodString(const std::string &s) {
+    float var = 1.f;
+    if (std::sscanf(s.c_str(), "VAQ%dm%dmin%dmax%dvar%f", &mBitBudget, &mSubspaceNum, &mMinBitsPerSubs, &mMaxBitsPerSubs, &var) < 4)
+      throw std::runtime_error("parseMethodString: expected VAQ<budget>m<M>min<a>max<b>var<v>,<MODE>");
+    mPercentVarExplained = var;
+    mMethods = 0;
+    const size_t comma = s.find(',');
+    const std::string mode = comma == std::string::npos ? "" : s.substr(comma + 1);
+    if (mode.find("FAST") != std::string::npos) throw std::runtime_error("FAST* modes are not provided (lossy uint8 LUT)");
+    if (mode.find("SORT") != std::string::npos) mMethods |= Sort;
+    if (mode.find("HEAP") != std::string::npos) mMethods |= Heap;
+    if (mode.find("EA") != std::string::npos) mMethods |= EA;
+    const size_t ti = mode.find("TI");
+    if (ti != std::string::npos) {
+      mMethods |= TI;
+      std::sscanf(mode.c_str() + ti, "TI%d", &mTIClusterNum);
+    }
+    if (!mMethods) mMethods = Heap;
+  }
+
+  // Hand over what VAQ::train produced (public members VAQ.hpp:57-73): mSubsLen, mHighestSubs, mBitsAlloc,
+  // mCentroidsPerSubs (concatenated row-major [2^bits[s] x L] blocks), real(mEigenVectors) [D x D] or nullptr.
+  void loadModel(int subsLen, int highestSubs, const int *bitsAlloc, const float *centroidsPerSubs, const float *eigReal) {
+    vaqgpu_destroy(h_);
+    h_ = nullptr;
+    mSubsLen = subsLen;
+    mHighestSubs = highestSubs;
+    vaqgpu_model_desc d;
+    d.D = subsLen * highestSubs; d.M = highestSubs; d.L = subsLen;
+    d.bits = bitsAlloc; d.centroids = centroidsPerSubs; d.eig_real = eigReal;
+    check(vaqgpu_create(&d, device_, &h_));
+    has_eig_ = eigReal != nullptr;
+  }
+
+  // mCodebook (VAQ.hpp:72): row-major [n x mHighestSubs] uint16, as VAQ::encode left it on the host
+  void setCodebook(const uint16_t *codes, int64_t n) { check(vaqgpu_add_codes_u16(need(), codes, n)); }
+
+  // VAQ::encode (VAQ.cpp:663): rows must already be projected (train() projects in place)
+  void encode(const float *XTrainProjected, int64_t n) { check(vaqgpu_encode_add(need(), XTrainProjected, n)); }
+
+  // VAQ::clusterTI's outputs (VAQ.hpp:77-84) for the TI / visit mode
+  void setClusters(const float *clusters, int C, int segdims, const int64_t *start, const int64_t *size, const int32_t *members) {
+    check(vaqgpu_set_clusters(need(), clusters, C, segdims, start, size, members));
+  }
+
+  // VAQ::search (VAQ.cpp:776-847): XTest is raw [nq x D] when the model has eigenvectors, else projected
+  LabelDistVecF search(const float *XTest, int nq, int k, bool /*verbose*/ = false) {
+    LabelDistVecF ret;
+    ret.labels.resize((size_t)nq * k);
+    ret.distances.resize((size_t)nq * k);
+    uint32_t flags = has_eig_ ? 0u : VAQGPU_PROJECTED;
+    if (mMethods & TI) {
+      check(vaqgpu_set_visit(need(), mVisit));
+      flags |= VAQGPU_TI | VAQGPU_EA | VAQGPU_SQRT;        // TI returns sqrt distances and original ids (VAQ.cpp:1585-1607)
+    } else if (mMethods & EA) {
+      flags |= VAQGPU_EA;
+    } else {
+      flags |= VAQGPU_HEAP;
+    }
+    check(vaqgpu_search(need(), XTest, nq, k, flags, ret.labels.data(), ret.distances.data()));
+    return ret;
+  }
+
+  // VAQ::refine (VAQ.cpp:849-876): XTrain raw rows [n x D0]; answersIn.labels holds refineNum candidates per query
+  LabelDistVecF refine(const float *XTest, int nq, const LabelDistVecF &answersIn, const float *XTrain, int64_t n, int D0, int k) {
+    if (XTrain != raw_ || n != raw_n_) {
+      check(vaqgpu_set_raw_vectors(need(), XTrain, n, D0));
+      raw_ = XTrain; raw_n_ = n;
+    }
+    const int refineNum = (int)(answersIn.labels.size() / (size_t)nq);
+    LabelDistVecF ret;
+    ret.labels.resize((size_t)nq * k);
+    ret.distances.resize((size_t)nq * k);
+    check(vaqgpu_refine(h_, XTest, nq, answersIn.labels.data(), refineNum, k, ret.labels.data(), ret.distances.data()));
+    return ret;
+  }
+
+  vaqgpu_t *handle() { return need(); }
+
+ private:
+  vaqgpu_t *need() {
+    if (!h_) throw std::runtime_error("vaqgpu::VAQ: loadModel() first");
+    return h_;
+  }
+  int device_;
+  vaqgpu_t *h_ = nullptr;
+  bool has_eig_ = false;
+  const float *raw_ = nullptr;
+  int64_t raw_n_ = 0;
+};
+
+class BitVecEngine {
+ public:
+  // BitVecEngine::QueryMethod, BitVecEngine.hpp:82-84.  Every method returns the k nearest rows; on the
+  // device they all run the same scan and equal-distance rows are ordered by ascending index.
+  enum QueryMethod { Heap = 0, Sort = 1, HeapEarlyAbandon = 2, SortEarlyAbandon = 3 };
+  const int N;
+  const int actBitVLen;
+
+  explicit BitVecEngine(int _N, int device = 0) : N(_N), actBitVLen((_N + 63) / 64) { check(hamgpu_create(_N, device, &h_)); }
+  ~BitVecEngine() { hamgpu_destroy(h_); }
+  BitVecEngine(const BitVecEngine &) = delete;
+  BitVecEngine &operator=(const BitVecEngine &) = delete;
+
+  // BitVecEngine::loadBitV / appendBitV (BitVecEngine.cpp:12, 1630)
+  void appendBitV(const bitvectors &bv) {
+    std::vector<uint64_t> flat = flatten(bv);
+    check(hamgpu_add(h_, flat.data(), (int64_t)bv.size()));
+  }
+  void loadBitV(const bitvectors &bv) {
+    int64_t n = 0;
+    check(hamgpu_num_rows(h_, &n));
+    if (n != 0) throw std::runtime_error("loadBitV on a non-empty engine: create a new engine (rows are append-only on the device)");
+    appendBitV(bv);
+  }
+  int64_t size() const {
+    int64_t n = 0;
+    check(hamgpu_num_rows(h_, &n));
+    return n;
+  }
+
+  // BitVecEngine::query (BitVecEngine.cpp:509-519) / queryParallel (:1264-1304)
+  std::vector<std::vector<IdxDistPair>> query(const bitvectors &queries, int k, int /*method*/ = Sort) const {
+    const int nq = (int)queries.size();
+    std::vector<uint64_t> flat = flatten(queries);
+    std::vector<int32_t> idx((size_t)nq * k);
+    std::vector<uint32_t> dist((size_t)nq * k);
+    check(hamgpu_query(h_, flat.data(), nq, k, idx.data(), dist.data()));
+    std::vector<std::vector<IdxDistPair>> out((size_t)nq);
+    for (int q = 0; q < nq; q++) {
+      for (int j = 0; j < k; j++) {
+        if (idx[(size_t)q * k + j] < 0) break;      // fewer than k rows
+        out[(size_t)q].push_back(IdxDistPair{idx[(size_t)q * k + j], dist[(size_t)q * k + j]});
+      }
+    }
+    return out;
+  }
+  std::vector<std::vector<IdxDistPair>> queryParallel(const bitvectors &queries, int k, int /*thread*/) const { return query(queries, k); }
+
+ private:
+  std::vector<uint64_t> flatten(const bitvectors &bv) const {
+    std::vector<uint64_t> flat(bv.size() * (size_t)actBitVLen, 0);
+    for (size_t i = 0; i < bv.size(); i++) {
+      if ((int)bv[i].size() != actBitVLen) throw std::runtime_error("bit vector length does not match the engine");
+      for (int w = 0; w < actBitVLen; w++) flat[i * (size_t)actBitVLen + (size_t)w] = bv[i][(size_t)w];
+    }
+    return flat;
+  }
+  hamgpu_t *h_ = nullptr;
+};
+
+}  // namespace vaqgpu

@@ -1,0 +1,84 @@
+"""CPU: host-side logic — method-string parsing, bit allocation, trainer, synthetic generators, sharding helpers."""
+import numpy as np
+import pytest
+
+from helpers import orc
+from vaq_b200 import synth, train
+from vaq_b200.sharded import make_keys_f32, make_keys_u32, shard_bounds, split_keys
+
+
+def test_parse_method_string():
+    p = train.parse_method_string("VAQ256m32min7max13var1,EA_TI1000")     # scripts/run_demos.sh-style strings
+    assert (p["budget"], p["M"], p["min_bits"], p["max_bits"], p["var"]) == (256, 32, 7, 13, 1.0)
+    assert p["methods"] == {"EA", "TI"} and p["ti_clusters"] == 1000
+    p = train.parse_method_string("VAQ128m16min6max10var1,HEAP")
+    assert p["methods"] == {"HEAP"} and p["budget"] == 128
+    with pytest.raises(ValueError):
+        train.parse_method_string("VAQ64m16min1max4var1,FAST")
+
+
+def brute_force_alloc(v, budget, lo, hi):
+    import itertools
+    best, arg = -1, None
+    kd = [max(train.next_pow2(v[i] / v[i + 1]), 0) for i in range(len(v) - 1)]
+    for x in itertools.product(range(lo, hi + 1), repeat=len(v)):
+        if sum(x) != budget or any(x[i] - x[i + 1] > kd[i] for i in range(len(v) - 1)):
+            continue
+        val = sum(a * b for a, b in zip(v, x))
+        if val > best + 1e-12:
+            best, arg = val, x
+    return best, arg
+
+
+def test_allocate_bits_is_optimal_for_the_reference_ilp():
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        v = np.sort(rng.random(5))[::-1] + 0.05
+        v /= v.sum()
+        budget = int(rng.integers(12, 28))
+        bits = train.allocate_bits(v, budget, 2, 7)
+        best, arg = brute_force_alloc(v, budget, 2, 7)
+        assert bits.sum() == budget and bits.min() >= 2 and bits.max() <= 7
+        assert abs(float((v * bits).sum()) - best) < 1e-9, (bits, arg)
+
+
+def test_train_shapes_and_descending_bits():
+    X = synth.decaying_gaussian(3000, 32, seed=3)
+    model, XP = train.train(X, 64, 8, 5, 10, kmeans_iters=3)
+    assert model.L == 4 and model.bits.sum() == 64 and model.D == 32
+    assert all(c.shape == (1 << int(b), 4) for c, b in zip(model.centroids, model.bits))
+    assert (np.diff(model.bits) <= 0).all()           # variance-descending subspaces get at least as many bits
+    np.testing.assert_allclose(XP, X @ model.eig, rtol=1e-5, atol=1e-5)
+    codes = train.encode_host(model, XP[:200])
+    om = orc.Model(model.L, model.bits, model.centroids)
+    assert (codes == orc.Port().encode(om, XP[:200])).mean() > 0.999
+
+
+def test_synthetic_generators_are_counter_based():
+    bits = [9, 4, 7, 1]
+    a = synth.synth_codes(bits, 1000, 5000, 42)
+    b = synth.synth_codes(bits, 100, 5500, 42)
+    assert np.array_equal(a[500:600], b)                  # any row slice regenerates identically
+    assert (a.max(0) < (1 << np.array(bits))).all()
+    cdf = synth.code_cdf(a, bits)
+    c = synth.synth_codes(bits, 20000, 0, 7, cdf)
+    h = np.bincount(c[:, 0], minlength=512) / 20000
+    h0 = np.bincount(a[:, 0], minlength=512) / 1000
+    assert np.abs(h - h0).max() < 0.01
+    w = synth.synth_bitvectors(50, 10, 100, 3)
+    assert w.shape == (50, 2) and (w[:, 1] >> np.uint64(36)).max() == 0
+    assert np.array_equal(synth.synth_bitvectors(10, 30, 100, 3), w[20:30])
+
+
+def test_shard_bounds_and_key_format():
+    assert shard_bounds(10, 4) == [0, 3, 6, 9, 10]
+    assert shard_bounds(8, 8)[-1] == 8 and shard_bounds(3, 8) == [0, 1, 2, 3, 3, 3, 3, 3, 3]
+    d = np.array([0.0, 1.5, 1.5, 3.0e38], np.float32)
+    ids = np.array([7, 2, 1, 2 ** 31 - 1], np.int32)
+    keys = make_keys_f32(d, ids)
+    order = np.argsort(keys)
+    assert order.tolist() == [0, 2, 1, 3]                 # ascending (distance, id)
+    i2, d2 = split_keys(keys)
+    assert np.array_equal(i2, ids) and np.array_equal(d2, d)
+    hk = make_keys_u32(np.array([3, 3, 1]), np.array([5, 4, 9]))
+    assert np.argsort(hk).tolist() == [2, 1, 0]

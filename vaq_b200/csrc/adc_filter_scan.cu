@@ -112,6 +112,38 @@ __device__ __forceinline__ bool score_fields(const uint32_t *__restrict__ rp, co
   return true;
 }
 
+// Exact distances of one row (per lane) to all T queries of the tile, same summation order as above.
+template <int T>
+__device__ __forceinline__ void score_row_all(const uint32_t *__restrict__ rp, const ScanLayout &lay, const float *__restrict__ slut,
+                                              const float *__restrict__ gspill, float (&dist)[T]) {
+  const int M = lay.M;
+#pragma unroll
+  for (int t = 0; t < T; t++) dist[t] = 0.f;
+  for (int g = 0; g < M; g += 4) {
+    float dism[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) dism[t] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int f = g + j;
+      if (f < M) {
+        const uint32_t meta = lay.fmeta[f];
+        const uint32_t lo = __ldg(rp + lay.fw_lo[f]), hi = __ldg(rp + lay.fw_hi[f]);
+        const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
+        const uint32_t idx = (lay.foff[f] + code) * T;
+        float v[T];
+        if (meta & kFieldSpill) ldg_vec<T>(v, gspill + idx);
+        else lds_vec<T>(v, slut + idx);
+#pragma unroll
+        for (int t = 0; t < T; t++) dism[t] += v[t];
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; t++) dist[t] += dism[t];
+  }
+}
+
+constexpr int kSeedRowsPerLane = 4;   // bound seeding: nwarps * 32 * 4 sample rows per CTA
 constexpr int kQ2Cap = 64;                                         // 31 pending + one level-1 drain
 
 template <int W, int T>
@@ -175,6 +207,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   const bool two_level = M > 8;
   const int F2 = two_level ? 8 : M;
 
+  const unsigned qmask = (a.nq - q0 >= T) ? ((1u << T) - 1u) : ((1u << (a.nq - q0)) - 1u);   // real queries of this tile
   uint32_t *q1 = queues + (size_t)warp * (kQ1Cap + 2 * kQ2Cap);
   uint32_t *q2e = q1 + kQ1Cap;
   float *q2d = reinterpret_cast<float *>(q2e + kQ2Cap);
@@ -212,7 +245,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
     const bool valid = row < a.n_rows;
     unsigned sb = 0;
 #pragma unroll
-    for (int t = 0; t < T; t++) sb |= (valid && !(dism[t] > thr[t]) && (q0 + t < a.nq)) ? (1u << t) : 0u;
+    for (int t = 0; t < T; t++) sb |= !(dism[t] > thr[t]) ? (1u << t) : 0u;
+    sb = valid ? (sb & qmask) : 0u;
     if (__any_sync(0xffffffffu, sb != 0)) {
       const uint32_t rel = (uint32_t)(row - row_base) << 3;
 #pragma unroll
@@ -223,6 +257,53 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
       }
     }
   };
+
+  // ---- bound seeding ---------------------------------------------------------------------------------
+  // A CTA that starts without a k-th-best bound would have to score everything it sees.  Each warp
+  // scores a few sample rows of the chunk exactly for all T queries and keeps the minimum per query:
+  // the k-th smallest of the nwarps minima is the distance of k distinct rows, hence a valid bound.
+  if (a.seed && k <= nwarps && (tile_end - tile_begin) * kTileRows >= (int64_t)blockDim.x * kSeedRowsPerLane * 8) {
+    float *wmin = reinterpret_cast<float *>(q1);      // the warp's queue space is still free
+    const int64_t rows_here = min(a.n_rows, tile_end << 5) - row_base;
+    const int64_t step = rows_here / ((int64_t)blockDim.x * kSeedRowsPerLane);
+    float best[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) best[t] = __uint_as_float(0x7f800000u);
+    for (int j = 0; j < kSeedRowsPerLane; j++) {
+      const int64_t row = row_base + ((int64_t)(j * (int)blockDim.x + tid)) * step;
+      const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
+      float d[T];
+      score_row_all<T>(rp, a.lay, slut, gspill, d);
+#pragma unroll
+      for (int t = 0; t < T; t++) best[t] = fminf(best[t], d[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best[t] = fminf(best[t], __shfl_xor_sync(0xffffffffu, best[t], o));
+    }
+    __syncthreads();
+    float *allmin = reinterpret_cast<float *>(queues);   // [nwarps][T], rows of different warps' queue space: use warp 0's
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < T; t++) allmin[warp * T + t] = best[t];
+    }
+    __syncthreads();
+    if (tid < T) {
+      // k-th smallest of the nwarps minima (rank by counting; ties broken by index)
+      const float *col = allmin + tid;
+      float kth = __uint_as_float(0x7f800000u);
+      for (int i = 0; i < nwarps; i++) {
+        const float x = col[i * T];
+        int rank = 0;
+        for (int j = 0; j < nwarps; j++) rank += (col[j * T] < x) || (col[j * T] == x && j < i);
+        if (rank == k - 1) kth = x;
+      }
+      atomicMin(thr_f + tid, __float_as_uint(kth));
+    }
+    __syncthreads();
+    (void)wmin;
+  }
 
   int64_t tl = tile_begin + warp;
   uint4 bA = make_uint4(0, 0, 0, 0), bB = bA;
@@ -321,77 +402,6 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
     const int q = q0 + t;
     if (q < a.nq) a.out_keys[((size_t)q * a.out_slots + a.slot_base + chunk) * k + j] = lists[i];
   }
-}
-
-// ---- bound seeding ------------------------------------------------------------------------------------
-// One CTA per query: scores kSample rows spread evenly over the index exactly (same summation order as
-// the scan), sorts the distances and publishes the k-th smallest as the query's initial bound.  Any k
-// rows give a valid bound (the true k-th best can only be smaller), so the scan that follows can prune
-// from its first tile instead of scoring everything until its own lists fill.
-constexpr int kSample = 4096;
-
-__global__ void __launch_bounds__(1024) adc_seed_bounds_kernel(const __grid_constant__ AdcSeedArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t *vals = reinterpret_cast<uint32_t *>(smem_raw);                 // [kSample]
-  float *slut = reinterpret_cast<float *>(vals + kSample);                 // [lut_stride] this query's tables
-  const int q = blockIdx.x, T = a.T;
-  const float *glut = a.lut + (size_t)(q / T) * a.lut_stride * T + (q % T);
-  for (int i = threadIdx.x; i < a.lut_stride; i += blockDim.x) slut[i] = __ldg(glut + (size_t)i * T);
-  __syncthreads();
-  const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
-  const int W = a.lay.W, M = a.lay.M;
-  const int64_t step = a.n_rows / kSample;
-  for (int i = threadIdx.x; i < kSample; i += blockDim.x) {
-    const int64_t row = (int64_t)i * step;
-    const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
-    float dist = 0.f;
-    for (int g = 0; g < M; g += 4) {
-      float dism = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int f = g + j;
-        if (f < M) {
-          const uint32_t meta = a.lay.fmeta[f];
-          const uint32_t lo = __ldg(rp + a.lay.fw_lo[f]), hi = __ldg(rp + a.lay.fw_hi[f]);
-          const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
-          const uint32_t base = (meta & kFieldSpill) ? (uint32_t)a.smem_lut_floats : 0u;
-          dism += slut[base + a.lay.foff[f] + code];
-        }
-      }
-      dist += dism;
-    }
-    vals[i] = __float_as_uint(dist);
-  }
-  __syncthreads();
-  // bitonic sort, ascending (distances are non-negative: the bit patterns order like the floats)
-  for (int size = 2; size <= kSample; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < kSample / 2; i += blockDim.x) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const uint32_t x = vals[lo], y = vals[hi];
-        if ((x > y) == up) { vals[lo] = y; vals[hi] = x; }
-      }
-      __syncthreads();
-    }
-  }
-  if (threadIdx.x == 0) atomicMin(a.thr_global + q, vals[a.k - 1]);
-}
-
-int adc_seed_sample_rows() { return kSample; }
-
-cudaError_t launch_adc_seed_bounds(const AdcSeedArgs &a, cudaStream_t st) {
-  if (a.nq <= 0) return cudaSuccess;
-  const size_t smem = (size_t)kSample * 4 + (size_t)a.lut_stride * 4;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(adc_seed_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  adc_seed_bounds_kernel<<<a.nq, 1024, smem, st>>>(a);
-  return cudaGetLastError();
 }
 
 size_t adc_filter_smem_bytes(int smem_lut_floats, int T, int k, int threads) {

@@ -185,19 +185,9 @@ struct AdcFilterArgs {
   int32_t slot_base;         // this launch's first list
   uint64_t *out_keys;        // [nq][out_slots][k]; low word = LOCAL row index
   uint32_t *thr_global;      // [nq] float bits of the best known k-th distance (0xFFFFFFFF = none)
+  int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
   ScanLayout lay;
 };
-struct AdcSeedArgs {
-  const uint4 *codes;
-  int64_t n_rows;
-  const float *lut;          // interleaved LUT workspace
-  int32_t lut_stride, smem_lut_floats, T;
-  int32_t nq, k;
-  uint32_t *thr_global;
-  ScanLayout lay;
-};
-int adc_seed_sample_rows();
-cudaError_t launch_adc_seed_bounds(const AdcSeedArgs &a, cudaStream_t st);
 size_t adc_filter_smem_bytes(int smem_lut_floats, int T, int k, int threads);
 cudaError_t launch_adc_filter_scan(const AdcFilterArgs &a, int T, int threads, size_t smem_bytes, cudaStream_t st);
 cudaError_t launch_fill_u32(uint32_t *p, int n, uint32_t v, cudaStream_t st);

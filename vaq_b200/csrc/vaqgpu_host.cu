@@ -5,6 +5,7 @@
 #include <float.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -255,6 +256,20 @@ __global__ void ham_pad_queries_kernel(const uint64_t *__restrict__ q, int nq, i
   out[i] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
 }
 
+// Development knobs (benchmark sweeps only): VAQGPU_TUNE="seed=0,T=2,chunks=4,threads=512"
+int tune_knob(const char *name, int dflt) {
+  const char *e = getenv("VAQGPU_TUNE");
+  if (!e) return dflt;
+  const size_t n = strlen(name);
+  for (const char *p = e; *p;) {
+    if (!strncmp(p, name, n) && p[n] == '=') return atoi(p + n + 1);
+    const char *c = strchr(p, ',');
+    if (!c) break;
+    p = c + 1;
+  }
+  return dflt;
+}
+
 // The whole device-side search; exactly one of (d_labels,d_dists) / d_keys is the output.
 //
 // Scan kernel selection (the reference dispatches TI -> EA -> HEAP, VAQ.cpp:799-840):
@@ -293,8 +308,9 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
 
   if (filter) {
     // ---- query-tile width T and residency -------------------------------------------------------
-    const int threads = 1024;
+    const int threads = tune_knob("threads", 1024);
     int T = nq >= 8 ? 8 : (nq >= 3 ? 4 : nq);
+    T = std::min(T, tune_knob("T", 8));
     for (;; T >>= 1) {
       const size_t fixed = adc_filter_smem_bytes(0, T, k, threads) + 1024;
       if (fixed >= kSmemCap) {
@@ -320,15 +336,11 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     int64_t n_chunks = std::max<int64_t>(1, (target + qtiles_first - 1) / qtiles_first);
     n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16)));
     n_chunks = std::max<int64_t>(n_chunks, (n_tiles + 32767) / 32768);          // <= 1M rows per chunk
+    n_chunks = tune_knob("chunks", (int)n_chunks);
     int64_t chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
     n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     if (n_chunks > 65535) return fail(VAQGPU_EINVAL, "index too large for one launch (%lld chunks)", (long long)n_chunks);
 
-    // Bound seeding: a CTA that starts with no k-th-best bound has to score everything it sees, so a
-    // small kernel first scores a fixed sample of rows per query and publishes the k-th smallest.
-    const int sample = adc_seed_sample_rows();
-    const bool seed = h->n_rows >= 8 * (int64_t)sample && k <= sample / 4 &&
-                      (size_t)sample * 4 + (size_t)plan.row_stride * 4 <= kSmemCap;
     const int n_warm = 0;
     const int out_slots = (int)n_chunks + n_warm;
 
@@ -352,14 +364,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.out_keys = (uint64_t *)h->w_keys.p;
       a.thr_global = (uint32_t *)h->w_thr.p;
       a.lay = lay;
-      if (seed) {
-        AdcSeedArgs sa{};
-        sa.codes = h->d_codes; sa.n_rows = h->n_rows; sa.lut = (const float *)h->w_lut.p;
-        sa.lut_stride = plan.row_stride; sa.smem_lut_floats = res_floats; sa.T = T; sa.nq = qb; sa.k = k;
-        sa.thr_global = (uint32_t *)h->w_thr.p; sa.lay = lay;
-        CU(launch_adc_seed_bounds(sa, st));
-        launches++;
-      }
+      a.seed = tune_knob("seed", 1);
       a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles; a.slot_base = n_warm;
       CU(launch_adc_filter_scan(a, T, threads, smem, st));
       launches++;
@@ -372,7 +377,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
     h->cfg[0] = threads; h->cfg[1] = (int32_t)n_chunks; h->cfg[2] = res_floats; h->cfg[3] = spill_floats;
     h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
-    h->cfg[8] = T; h->cfg[9] = 2; h->cfg[10] = seed ? sample : 0;
+    h->cfg[8] = T; h->cfg[9] = 2; h->cfg[10] = 0;
     return VAQGPU_OK;
   }
 

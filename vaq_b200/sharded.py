@@ -41,12 +41,14 @@ def allgather_keys(local_keys, group=None):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    out = torch.empty((world,) + tuple(local_keys.shape), dtype=local_keys.dtype, device=local_keys.device)
+    local_keys = local_keys.contiguous()
+    flat = torch.empty((world * local_keys.shape[0],) + tuple(local_keys.shape[1:]), dtype=local_keys.dtype,
+                       device=local_keys.device)
     if world == 1:
-        out[0].copy_(local_keys)
+        flat.copy_(local_keys)
     else:
-        dist.all_gather_into_tensor(out, local_keys.contiguous(), group=group)
-    return out
+        dist.all_gather_into_tensor(flat, local_keys, group=group)     # concatenation along dim 0 == [G][nq][k]
+    return flat.view((world,) + tuple(local_keys.shape))
 
 
 class ShardedVAQ:
