@@ -303,7 +303,7 @@ def run_gpu_arm(args, w, name):
     scan_ms_mean = float(np.mean(scan_ms))
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes_step / (scan_ms_mean / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "adc_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "adc_filter_scan_kernel" if cfg["scan_kernel"] == 2 else "adc_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
                 "launch_ms": scan_ms_mean / n_launch, "query_tile_T": T,
                 "pairs_per_s": nq * n_local / (scan_ms_mean / 1e3),
@@ -313,6 +313,7 @@ def run_gpu_arm(args, w, name):
 
     # ---- the same kernel on a shard far larger than L2 (the HBM-bound regime of the 100M / 1B-row shapes)
     hbm_shape = None
+    hamming = None
     if not args.no_hbm_shape:
         try:
             big_n = args.hbm_rows
@@ -320,25 +321,52 @@ def run_gpu_arm(args, w, name):
             big.reserve(big_n)
             cdf = synth.code_cdf(ix.get_codes(0, min(n_local, 200_000)), model.bits)
             big.add_synthetic(big_n, SEED, cdf)
-            bq = 64
-            lab = torch.empty((bq, k), dtype=torch.int32, device=dev)
-            dis = torch.empty((bq, k), dtype=torch.float32, device=dev)
-            ms = []
-            for i in range(3 + 5):
-                big.search_device(d_q.data_ptr(), bq, k, flags, lab.data_ptr(), dis.data_ptr(), st.cuda_stream)
-                torch.cuda.synchronize()
-                if i >= 3:
-                    ms.append(big.last_timings()["scan_ms"])
-            bcfg = big.last_config()
-            bT = max(1, bcfg["queries_per_cta"])
-            b = -(-bq // bT) * big_n * row_bytes + bq * lut_bytes
-            a = b / (np.mean(ms) / 1e3) / 1e9
-            hbm_shape = {"rows": big_n, "queries": bq, "packed_bytes": big_n * row_bytes, "scan_ms": float(np.mean(ms)),
-                         "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "query_tile_T": bT,
-                         "pairs_per_s": bq * big_n / (np.mean(ms) / 1e3), "config": bcfg}
+            hbm_shape = {"rows": big_n, "packed_bytes": big_n * row_bytes, "peak": peak, "unit": "GB/s", "runs": []}
+            for bq in (4, 64):
+                lab = torch.empty((bq, k), dtype=torch.int32, device=dev)
+                dis = torch.empty((bq, k), dtype=torch.float32, device=dev)
+                ms = []
+                for i in range(3 + 5):
+                    flush.fill_(i)
+                    big.search_device(d_q.data_ptr(), bq, k, flags, lab.data_ptr(), dis.data_ptr(), st.cuda_stream)
+                    torch.cuda.synchronize()
+                    if i >= 3:
+                        ms.append(big.last_timings()["scan_ms"])
+                bcfg = big.last_config()
+                bT = max(1, bcfg["queries_per_cta"])
+                b = -(-bq // bT) * big_n * row_bytes + bq * lut_bytes
+                a = b / (np.mean(ms) / 1e3) / 1e9
+                hbm_shape["runs"].append({"queries": bq, "query_tile_T": bT, "scan_ms": float(np.mean(ms)), "achieved": a,
+                                          "frac": a / peak, "first_word_stream_GBps": -(-bq // bT) * big_n * 16 / (np.mean(ms) / 1e3) / 1e9,
+                                          "pairs_per_s": bq * big_n / (np.mean(ms) / 1e3), "config": bcfg})
             big.close()
         except Exception as e:      # never hide the headline behind the auxiliary leg
             hbm_shape = {"error": repr(e)}
+        try:
+            from vaq_b200.index import HammingIndex
+            hn, hq = args.hbm_rows, 64
+            hx = HammingIndex(256, device=local_rank)
+            hx.add_synthetic(hn, SEED)
+            hqv = torch.from_numpy(synth.synth_bitvectors(hq, 10 ** 10, 256, SEED).view(np.int64)).to(dev)
+            hidx = torch.empty((hq, k), dtype=torch.int32, device=dev)
+            hdist = torch.empty((hq, k), dtype=torch.int32, device=dev)
+            ms = []
+            for i in range(3 + 5):
+                flush.fill_(i)
+                hx.query_device(hqv.data_ptr(), hq, k, hidx.data_ptr(), hdist.data_ptr(), st.cuda_stream)
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ms.append(hx.last_timings()["scan_ms"])
+            hcfg = hx.last_config()
+            qt = max(1, hcfg["queries_per_cta"])
+            b = -(-hq // qt) * hn * 32
+            a = b / (np.mean(ms) / 1e3) / 1e9
+            hamming = {"kernel": "ham_scan_kernel", "rows": hn, "bits": 256, "queries": hq, "queries_per_pass": qt,
+                       "scan_ms": float(np.mean(ms)), "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                       "qps": hq / (np.mean(ms) / 1e3), "config": hcfg}
+            hx.close()
+        except Exception as e:
+            hamming = {"error": repr(e)}
 
     # ---- CPU baseline on the box's host cores + parity of the returned neighbours on the same queries
     cpu = None
@@ -371,6 +399,7 @@ def run_gpu_arm(args, w, name):
         "clocks": clocks,
         "roofline": roofline,
         "roofline_hbm_shape": hbm_shape,
+        "hamming_scan": hamming,
         "cpu_baseline": cpu,
         "parity_vs_cpu": parity,
         "kernel_ms": {"lut_build": float(np.mean(lut_ms)), "adc_scan": scan_ms_mean, "merge": float(np.mean(merge_ms))},
