@@ -44,6 +44,7 @@ extern "C" {
 #define VAQGPU_PROJECTED 0x100u /* queries are already in PCA space: skip (X*V).real(), VAQ.cpp:777 */
 #define VAQGPU_SQRT 0x200u      /* return sqrt(ADC) as the TI mode does (VAQ.cpp:1585) */
 #define VAQGPU_SCAN_V1 0x1000u  /* diagnostics: force the lane-per-row scan kernel for EA searches */
+#define VAQGPU_SCAN_F32 0x2000u /* diagnostics: force the fp32-table filter kernel (skip the fp16 lower-bound tables) */
 
 typedef struct vaqgpu_index vaqgpu_t;
 typedef struct hamgpu_index hamgpu_t;
@@ -142,7 +143,8 @@ int vaqgpu_last_timings(const vaqgpu_t *h, float ms[4]);
 /* Scan configuration chosen for the last search: [0]=threads/CTA, [1]=row chunks (CTAs per query tile),
  * [2]=LUT entries per query resident in shared memory, [3]=LUT entries spilled to L2, [4]=dynamic smem
  * bytes, [5]=uint4 words per row, [6]=kernel launches of the last search, [7]=queries per launch,
- * [8]=queries per CTA (tile width T), [9]=scan kernel (1 = lane-per-row, 2 = filter-and-refine). */
+ * [8]=queries per CTA (tile width T), [9]=scan kernel (1 = lane-per-row, 2 = filter-and-refine on fp32
+ * tables, 3 = filter-and-refine on fp16 lower-bound tables). */
 int vaqgpu_last_config(const vaqgpu_t *h, int32_t cfg[12]);
 
 /* ---- BitVecEngine Hamming index ---------------------------------------- */

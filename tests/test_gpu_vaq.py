@@ -129,9 +129,10 @@ def check_search(port, m, codes, Q, k, flags, ix=None, id_base=0):
         ix = make_index(m, codes=codes)
         if id_base:
             ix.set_id_base(id_base)
-    from vaq_b200.index import SCAN_V1
+    from vaq_b200.index import SCAN_F32, SCAN_V1
     want_lab, want_dis = port.search_lex(m, codes, Q, k, id_base)
-    for extra, kern in ((0, None), (SCAN_V1, 1)):       # default kernel choice, then the lane-per-row kernel
+    # default kernel choice (fp16 lower-bound filter when it fits), the fp32 filter kernel, the lane-per-row kernel
+    for extra, kern in ((0, None), (SCAN_F32, None), (SCAN_V1, 1)):
         lab, dis = ix.search(Q, k, flags | PROJECTED | extra)
         assert np.array_equal(lab, want_lab), f"ids differ from the canonical (distance, id) top-k (extra={extra:#x})"
         assert bitwise_equal(dis, want_dis), "distances are not bit-identical to the oracle's summation order"
@@ -209,6 +210,33 @@ def test_search_multi_chunk_and_large_k(port):
     ix.close()
 
 
+def test_search_fp16_filter_extreme_scales(port):
+    """The fp16 lower-bound tables are rescaled per query: tiny and huge distance scales, zero tables."""
+    from vaq_b200.index import EA, PROJECTED
+    rng = np.random.default_rng(77)
+    bits = [8, 8, 7, 7, 6, 6, 5, 5, 4, 4, 4, 4]
+    for mult in (1e-12, 1e-4, 1.0, 3e4, 1e15):
+        cents = [(rng.standard_normal((1 << b, 3)) * mult * (1 + 5.0 / (1 + s))).astype(np.float32) for s, b in enumerate(bits)]
+        m = orc.Model(3, np.asarray(bits, np.int32), cents)
+        codes = random_codes(rng, m, 40000)
+        Q = (rng.standard_normal((9, m.D)) * mult * 2).astype(np.float32)
+        Q[3] = 0
+        ix = make_index(m, codes=codes)
+        check_search(port, m, codes, Q, 10, EA, ix=ix)
+        ix.search(Q, 10, EA | PROJECTED)
+        assert ix.last_config()["scan_kernel"] == 3
+        ix.close()
+    # all-zero tables for one subspace and a query equal to a centroid (exact zeros in the LUT)
+    cents = [rng.standard_normal((1 << b, 3)).astype(np.float32) for b in bits]
+    cents[0][:] = 0
+    m = orc.Model(3, np.asarray(bits, np.int32), cents)
+    codes = random_codes(rng, m, 20000)
+    Q = rng.standard_normal((8, m.D)).astype(np.float32)
+    Q[0] = np.concatenate([c[5 % c.shape[0]] for c in cents])
+    Q[:, :3] = 0
+    check_search(port, m, codes, Q, 10, EA)
+
+
 def test_search_duplicate_rows_tie_rule(port):
     """Exact ties: every row repeated 4x -> canonical order keeps the lowest ids."""
     from vaq_b200.index import EA
@@ -242,7 +270,7 @@ def test_search_spill_path(port):
     check_search(port, m, codes, Q, 10, EA, ix=ix)
     ix.search(Q, 10, EA | PROJECTED)
     cfg = ix.last_config()
-    assert cfg["spill_lut_floats"] > 0 and cfg["scan_kernel"] == 2, cfg
+    assert cfg["spill_lut_floats"] > 0 and cfg["scan_kernel"] == 2, cfg      # tables too large for the fp16 tile of 8
     check_search(port, m, codes, Q, 10, HEAP, ix=ix)
     assert ix.last_config()["spill_lut_floats"] > 0
     ix.close()

@@ -14,7 +14,7 @@ LIB_PATH = PKG / "libvaqgpu.so"
 
 VAQGPU_OK, VAQGPU_EINVAL, VAQGPU_ECUDA, VAQGPU_ENOMEM, VAQGPU_ESTATE = 0, -1, -2, -3, -4
 # search flags (include/vaqgpu.h; low byte == VAQ::NNMethod, reference VAQ.hpp:38-49)
-EA, TI, HEAP, PROJECTED, SQRT, SCAN_V1 = 0x02, 0x04, 0x80, 0x100, 0x200, 0x1000
+EA, TI, HEAP, PROJECTED, SQRT, SCAN_V1, SCAN_F32 = 0x02, 0x04, 0x80, 0x100, 0x200, 0x1000, 0x2000
 
 
 class VaqGpuError(RuntimeError):

@@ -1,0 +1,397 @@
+// ADC scan, filter-and-refine with half-precision lower-bound tables — the default kernel behind
+// VAQ::searchEarlyAbandon (reference bitvecengine/VAQ.cpp:1694-1727) when eight queries' tables fit in
+// shared memory as fp16.
+//
+// Same structure as adc_filter_scan.cu (stage 1 over every (row, query) pair on the first group of
+// subspaces, compacted survivors scored by full-lane warps), but the shared-memory tables hold
+//     e16[s][c][t] = round_toward_zero_fp16( scale_t * lut[t][s][c] ),     t = 0..7 (query tile of 8)
+// i.e. guaranteed LOWER bounds of the reference's table entries, 16 bytes per code for 8 queries.  One
+// LDS.128 therefore serves eight queries (the fp32 form serves four), which halves both the shared-memory
+// wavefronts and the instructions per pair — the two resources the fp32 form saturates (ncu: LSU 86 %,
+// issue 74 %).  Because the bounds are conservative, pruning stays exact:
+//
+//   stage 1   acc = e16_0 + e16_1 + e16_2 + e16_3 in packed half2 arithmetic (round-to-nearest: at most
+//             (1+2^-11)^3 above the real sum), pruned iff acc > RU_fp16(thr * scale * (1 + 2^-9)).  Then the real
+//             partial sum exceeds thr by > 2^-11 relative, far more than the 40 * 2^-24 by which the fp32
+//             distance the reference computes can fall below the real sum  =>  the reference's own distance
+//             is > thr and the row cannot be among the k best.
+//   level 1/2 per-lane lower bound over groups 1-2, then over all subspaces, accumulated in fp32 from the
+//             same fp16 entries, pruned iff LB > thr * scale * (1 + 2^-9).
+//   level 3   the few pairs whose full lower bound is still under the bound are scored EXACTLY from the
+//             fp32 tables in global memory (L2), in the reference's order and grouping
+//             (dism = ((l0+l1)+l2)+l3 ; dist += dism, VAQ.cpp:1741-1748), and only these exact distances
+//             enter the top-k lists and tighten the bounds.
+//
+// Result: bit-identical to the fp32 kernels (tests/test_gpu_vaq.py runs all three against the oracle).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace vaqgpu {
+
+namespace {
+
+constexpr int T8 = 8;
+constexpr int kQ1Cap16 = 32 + 32 * T8;   // 31 pending + one tile's pushes for 8 queries
+constexpr int kQCap = 64;                // level-2 / level-3 queues: 31 pending + one drain
+constexpr float kMargin = 1.0f + 1.0f / 512.0f;
+
+__device__ __forceinline__ uint32_t half_bits_ru(float x) { return (uint32_t)__half_as_ushort(__float2half_ru(x)); }
+
+__device__ __forceinline__ uint4 lds128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+
+__device__ __forceinline__ uint4 lds128_volatile(const void *p) {
+  uint4 r;
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+  return r;
+}
+
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+
+}  // namespace
+
+template <int W>
+__global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid_constant__ AdcFilter16Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int k = a.k;
+  const int qt = blockIdx.x, chunk = blockIdx.y;
+  const int q0 = qt * T8;
+
+  const size_t lut_bytes = (size_t)a.lut_stride * T8 * sizeof(__half);       // multiple of 64
+  const __half *slut = reinterpret_cast<const __half *>(smem_raw);
+  uint32_t *thr_f = reinterpret_cast<uint32_t *>(smem_raw + lut_bytes);      // [8] exact k-th distance bits (fp32)
+  uint32_t *thr_h = thr_f + 8;                                               // [8] fp16 bits of RU(thr * scale * margin)
+  float *scale_m = reinterpret_cast<float *>(thr_h + 8);                     // [8] scale * margin
+  uint32_t *locks = reinterpret_cast<uint32_t *>(scale_m + 8);               // [8]
+  uint64_t *lists = reinterpret_cast<uint64_t *>(locks + 8);                 // [8][k] ascending exact keys
+  uint64_t *bar = lists + (size_t)T8 * k;
+  uint32_t *queues = reinterpret_cast<uint32_t *>(bar + 1);                  // per warp: q1 | q2e | q2d | q3
+
+  const unsigned char *g16 = reinterpret_cast<const unsigned char *>(a.lut16) + (size_t)qt * lut_bytes;
+  const float *g32 = a.lut32 + (size_t)qt * a.lut_stride * T8;
+
+  for (int i = tid; i < T8 * k; i += blockDim.x) lists[i] = kEmptyKey;
+  if (tid < T8) {
+    const int q = min(q0 + tid, a.nq - 1);
+    const float sm = a.scale[q0 + tid] * kMargin;
+    const uint32_t g = a.thr_global[q];
+    scale_m[tid] = sm;
+    thr_f[tid] = g;
+    thr_h[tid] = half_bits_ru(__uint_as_float(g) * sm);
+    locks[tid] = 0u;
+  }
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar, (uint32_t)lut_bytes);
+    for (size_t off = 0; off < lut_bytes; off += 32768) {
+      const uint32_t n = (uint32_t)min((size_t)32768, lut_bytes - off);
+      tma_bulk_g2s(smem_raw + off, g16 + off, n, bar);
+    }
+  }
+  mbar_wait(bar, 0);
+
+  // stage-1 program: the first group (<= 4 fields, <= 60 bits, i.e. inside 32-bit words 0..2)
+  const int M = a.lay.M;
+  const int G1 = min(4, M);
+  uint32_t s1_sh[4], s1_mask[4], s1_off[4];
+  bool s1_hi[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int f = min(i, G1 - 1);
+    const uint32_t meta = a.lay.fmeta[f];
+    s1_sh[i] = meta & 31u;
+    s1_mask[i] = meta >> 16;
+    s1_off[i] = a.lay.foff[f] * (T8 * 2);          // byte offset of the table
+    s1_hi[i] = a.lay.fword[f] != 0;
+  }
+  const bool two_level = M > 8;
+  const int F2 = two_level ? 8 : M;
+
+  const unsigned qmask = (a.nq - q0 >= T8) ? 0xFFu : ((1u << (a.nq - q0)) - 1u);
+  uint32_t *q1 = queues + (size_t)warp * (kQ1Cap16 + 3 * kQCap);
+  uint32_t *q2e = q1 + kQ1Cap16;
+  float *q2d = reinterpret_cast<float *>(q2e + kQCap);
+  uint32_t *q3 = q2e + 2 * kQCap;
+  int q1n = 0, q2n = 0, q3n = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  const int64_t tile_begin = a.tile_lo + (int64_t)chunk * a.chunk_tiles;
+  const int64_t tile_end = min(a.tile_hi, tile_begin + a.chunk_tiles);
+  const int64_t row_base = tile_begin << 5;
+  const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
+
+  int64_t tl = tile_begin + warp;
+  uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+  if (tl < tile_end) cur = ldg_stream_u4(a.codes + ((size_t)tl * W) * kTileRows + lane);
+  if (tl + nwarps < tile_end) nxt = ldg_stream_u4(a.codes + ((size_t)(tl + nwarps) * W) * kTileRows + lane);
+  int refresh = 0;
+
+  while (true) {
+    const bool more = tl < tile_end;
+    int level = 0, take = 0;
+    if (q3n >= 32) { level = 3; take = 32; }
+    else if (q2n >= 32) { level = 2; take = 32; }
+    else if (q1n >= 32) { level = 1; take = 32; }
+    else if (!more) {
+      if (q1n > 0) { level = 1; take = q1n; }
+      else if (q2n > 0) { level = 2; take = q2n; }
+      else if (q3n > 0) { level = 3; take = q3n; }
+      else break;
+    }
+    if (level) {
+      // ---- survivors: one code site for the two lower-bound levels and the exact level ----------------
+      __syncwarp();
+      const bool active = lane < take;
+      uint32_t e = 0u;
+      float dist = 0.f;
+      int fb = 0, fe = M;
+      if (level == 1) {
+        if (active) e = q1[q1n - take + lane];
+        q1n -= take;
+        fe = F2;
+      } else if (level == 2) {
+        if (active) { e = q2e[q2n - take + lane]; dist = q2d[q2n - take + lane]; }
+        q2n -= take;
+        fb = F2;
+      } else {
+        if (active) e = q3[q3n - take + lane];
+        q3n -= take;
+      }
+      const bool exact = level == 3;
+      const int t = (int)(e & 7u);
+      const int64_t row = row_base + (e >> 3);
+      const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
+      float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
+      if (!exact) thr *= scale_m[t];
+      bool alive = true;
+      for (int g = fb; g < fe; g += 4) {
+        float dism = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int f = g + j;
+          if (f < fe) {
+            const uint32_t meta = a.lay.fmeta[f];
+            const uint32_t lo = __ldg(rp + a.lay.fw_lo[f]), hi = __ldg(rp + a.lay.fw_hi[f]);
+            const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
+            const uint32_t idx = (a.lay.foff[f] + code) * T8 + t;
+            dism += exact ? __ldg(g32 + idx) : __half2float(slut[idx]);
+          }
+        }
+        dist += dism;
+        if (__all_sync(0xffffffffu, !active || (dist > thr))) { alive = false; break; }
+      }
+      if (alive) {
+        if (!exact) {
+          // still under the bound: next level
+          const bool s = active && !(dist > thr);
+          const unsigned m = __ballot_sync(0xffffffffu, s);
+          const bool to_q2 = level == 1 && two_level;
+          if (s) {
+            if (to_q2) {
+              const int pos = q2n + __popc(m & lt_mask);
+              q2e[pos] = e;
+              q2d[pos] = dist;
+            } else {
+              q3[q3n + __popc(m & lt_mask)] = e;
+            }
+          }
+          if (to_q2) q2n += __popc(m); else q3n += __popc(m);
+        } else {
+          const uint64_t key = active ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
+          const uint64_t kth0 = active ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
+          unsigned m = __ballot_sync(0xffffffffu, key < kth0);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
+            const int tt = __shfl_sync(0xffffffffu, t, src);
+            volatile uint64_t *lst = lists + (size_t)tt * k;
+            {
+              uint64_t c = lst[k - 1];
+              c = __shfl_sync(0xffffffffu, c, 0);      // one observer: the decision must be warp-uniform
+              if (!(kk < c)) continue;
+            }
+            if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) __nanosleep(20);
+            __syncwarp();
+            const uint64_t before = lst[k - 1];
+            const uint64_t kth = warp_list_insert(lst, k, kk, lane);
+            __syncwarp();
+            if (lane == 0) {
+              __threadfence_block();
+              atomicExch(locks + tt, 0u);
+              if (kth != before && kth != kEmptyKey) {
+                const uint32_t bits = (uint32_t)(kth >> 32);
+                atomicMin(thr_f + tt, bits);
+                atomicMin(thr_h + tt, half_bits_ru(__uint_as_float(bits) * scale_m[tt]));
+                if (q0 + tt < a.nq) atomicMin(a.thr_global + q0 + tt, bits);
+              }
+            }
+          }
+        }
+      }
+      continue;
+    }
+
+    // ---- stage 1 on one tile ---------------------------------------------------------------------------
+    const uint4 w0 = cur;
+    cur = nxt;
+    {
+      const int64_t tn = tl + 2 * (int64_t)nwarps;
+      if (tn < tile_end) nxt = ldg_stream_u4(a.codes + ((size_t)tn * W) * kTileRows + lane);
+    }
+    if (((++refresh) & 31) == 0 && lane < T8 && q0 + lane < a.nq) {
+      // pick up bounds published by other row chunks of this query tile
+      const uint32_t g = *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane);
+      if (g < *reinterpret_cast<volatile uint32_t *>(thr_f + lane)) {
+        atomicMin(thr_f + lane, g);
+        atomicMin(thr_h + lane, half_bits_ru(__uint_as_float(g) * scale_m[lane]));
+      }
+    }
+    const uint4 th0 = lds128_volatile(thr_h), th1 = lds128_volatile(thr_h + 4);
+    const __half2 thr2[4] = {as_h2(__byte_perm(th0.x, th0.y, 0x5410)), as_h2(__byte_perm(th0.z, th0.w, 0x5410)),
+                             as_h2(__byte_perm(th1.x, th1.y, 0x5410)), as_h2(__byte_perm(th1.z, th1.w, 0x5410))};
+    __half2 acc[4];
+#pragma unroll
+    for (int i1 = 0; i1 < 4; i1++) {
+      if (i1 < G1) {
+        const uint32_t lo = s1_hi[i1] ? w0.y : w0.x, hi = s1_hi[i1] ? w0.z : w0.y;
+        const uint32_t code = __funnelshift_r(lo, hi, s1_sh[i1]) & s1_mask[i1];
+        const uint4 v = lds128(smem_raw + s1_off[i1] + code * (T8 * 2));
+        if (i1 == 0) { acc[0] = as_h2(v.x); acc[1] = as_h2(v.y); acc[2] = as_h2(v.z); acc[3] = as_h2(v.w); }
+        else {
+          acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
+          acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+        }
+      }
+    }
+    const int64_t row = (tl << 5) + lane;
+    unsigned sb = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned alive = ~__hgt2_mask(acc[j], thr2[j]);      // 0xFFFF per half that is NOT above its bound
+      sb |= ((alive & 1u) | ((alive >> 15) & 2u)) << (2 * j);
+    }
+    sb = (row < a.n_rows) ? (sb & qmask) : 0u;
+    if (__any_sync(0xffffffffu, sb != 0)) {
+      const uint32_t rel = (uint32_t)(row - row_base) << 3;
+#pragma unroll
+      for (int t = 0; t < T8; t++) {
+        const unsigned m = __ballot_sync(0xffffffffu, (sb >> t) & 1u);
+        if ((sb >> t) & 1u) q1[q1n + __popc(m & lt_mask)] = rel | (uint32_t)t;
+        q1n += __popc(m);
+      }
+    }
+    tl += nwarps;
+  }
+
+  // ---- CTA epilogue: publish this (query tile, chunk)'s keys -----------------------------------------
+  __syncthreads();
+  for (int i = tid; i < T8 * k; i += blockDim.x) {
+    const int t = i / k, j = i - t * k;
+    const int q = q0 + t;
+    if (q < a.nq) a.out_keys[((size_t)q * a.out_slots + a.slot_base + chunk) * k + j] = lists[i];
+  }
+}
+
+size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads) {
+  const int nwarps = threads / 32;
+  size_t b = (size_t)lut_stride * T8 * 2 + 4 * 32;
+  b += ((size_t)T8 * k + 1) * sizeof(uint64_t);
+  b += (size_t)nwarps * (kQ1Cap16 + 3 * kQCap) * sizeof(uint32_t);
+  return b;
+}
+
+template <int W>
+static cudaError_t launch16_w(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem_bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(adc_filter16_scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = smem_bytes;
+  }
+  const int64_t nt = a.tile_hi - a.tile_lo;
+  if (nt <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((a.nq + T8 - 1) / T8), (unsigned)((nt + a.chunk_tiles - 1) / a.chunk_tiles));
+  adc_filter16_scan_kernel<W><<<grid, threads, smem_bytes, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adc_filter16_scan(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
+  switch (a.lay.W) {
+    case 1: return launch16_w<1>(a, threads, smem_bytes, st);
+    case 2: return launch16_w<2>(a, threads, smem_bytes, st);
+    case 3: return launch16_w<3>(a, threads, smem_bytes, st);
+    case 4: return launch16_w<4>(a, threads, smem_bytes, st);
+    case 5: return launch16_w<5>(a, threads, smem_bytes, st);
+    case 6: return launch16_w<6>(a, threads, smem_bytes, st);
+    case 7: return launch16_w<7>(a, threads, smem_bytes, st);
+    case 8: return launch16_w<8>(a, threads, smem_bytes, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---- fp16 lower-bound tables ------------------------------------------------------------------------
+// One CTA per query tile: per-query maximum over the tile's fp32 tables -> power-of-two scale that puts
+// the largest entry in (8000, 16000] (four of them still sum below the fp16 maximum), then
+// e16 = round_toward_zero(scale * entry).  Entries past `n_entries` (alignment padding) become 0.
+__global__ void __launch_bounds__(256) lut16_build_kernel(const float *__restrict__ lut32, int lut_stride, int n_entries,
+                                                          __half *__restrict__ lut16, float *__restrict__ scale) {
+  __shared__ float smax[8][T8];
+  __shared__ float sscale[T8];
+  const int qt = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4 *src = reinterpret_cast<const float4 *>(lut32 + (size_t)qt * lut_stride * T8);
+  float m[T8];
+#pragma unroll
+  for (int t = 0; t < T8; t++) m[t] = 0.f;
+  for (int e = tid; e < n_entries; e += blockDim.x) {
+    const float4 a = __ldg(src + 2 * e), b = __ldg(src + 2 * e + 1);
+    m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
+    m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+  }
+#pragma unroll
+  for (int t = 0; t < T8; t++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[t] = fmaxf(m[t], __shfl_xor_sync(0xffffffffu, m[t], o));
+    if (lane == 0) smax[warp][t] = m[t];
+  }
+  __syncthreads();
+  if (tid < T8) {
+    float mx = 0.f;
+    for (int w = 0; w < 8; w++) mx = fmaxf(mx, smax[w][tid]);
+    float s = 1.f;
+    if (mx > 0.f && mx < 3.0e38f) {
+      int ex = (int)floorf(log2f(16000.f / mx));
+      ex = max(-100, min(100, ex));
+      s = exp2f((float)ex);
+      while (mx * s > 16000.f) s *= 0.5f;       // guard against log2f rounding at the boundary
+    }
+    sscale[tid] = s;
+    scale[qt * T8 + tid] = s;
+  }
+  __syncthreads();
+  uint4 *dst = reinterpret_cast<uint4 *>(lut16 + (size_t)qt * lut_stride * T8);
+  for (int e = tid; e < lut_stride; e += blockDim.x) {
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (e < n_entries) {
+      const float4 a = __ldg(src + 2 * e), b = __ldg(src + 2 * e + 1);
+      const __half2 h0 = __halves2half2(__float2half_rz(a.x * sscale[0]), __float2half_rz(a.y * sscale[1]));
+      const __half2 h1 = __halves2half2(__float2half_rz(a.z * sscale[2]), __float2half_rz(a.w * sscale[3]));
+      const __half2 h2 = __halves2half2(__float2half_rz(b.x * sscale[4]), __float2half_rz(b.y * sscale[5]));
+      const __half2 h3 = __halves2half2(__float2half_rz(b.z * sscale[6]), __float2half_rz(b.w * sscale[7]));
+      o = make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                     *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
+    }
+    dst[e] = o;
+  }
+}
+
+cudaError_t launch_lut16_build(const float *lut32, int n_qtiles, int lut_stride, int n_entries, void *lut16, float *scale,
+                               cudaStream_t st) {
+  if (n_qtiles <= 0) return cudaSuccess;
+  lut16_build_kernel<<<n_qtiles, 256, 0, st>>>(lut32, lut_stride, n_entries, reinterpret_cast<__half *>(lut16), scale);
+  return cudaGetLastError();
+}
+
+}  // namespace vaqgpu

@@ -192,6 +192,26 @@ size_t adc_filter_smem_bytes(int smem_lut_floats, int T, int k, int threads);
 cudaError_t launch_adc_filter_scan(const AdcFilterArgs &a, int T, int threads, size_t smem_bytes, cudaStream_t st);
 cudaError_t launch_fill_u32(uint32_t *p, int n, uint32_t v, cudaStream_t st);
 
+// filter-and-refine scan on fp16 lower-bound tables, query tiles of 8 (adc_filter16_scan.cu)
+struct AdcFilter16Args {
+  const uint4 *codes;
+  int64_t n_rows;
+  const void *lut16;         // [query tile][lut_stride][8] fp16: round-toward-zero(scale * entry)
+  const float *lut32;        // [query tile][lut_stride][8] fp32: the exact tables (read through L2 by the exact level)
+  const float *scale;        // [padded nq] power-of-two scale per query
+  int32_t lut_stride;        // entries per query
+  int32_t nq, k;
+  int64_t tile_lo, tile_hi;
+  int32_t chunk_tiles, out_slots, slot_base;
+  uint64_t *out_keys;
+  uint32_t *thr_global;
+  ScanLayout lay;
+};
+size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads);
+cudaError_t launch_adc_filter16_scan(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st);
+cudaError_t launch_lut16_build(const float *lut32, int n_qtiles, int lut_stride, int n_entries, void *lut16, float *scale,
+                               cudaStream_t st);
+
 // nq_launch >= nq queries are written (tile padding repeats the last query)
 cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, const float *centroids,
                              const LutPlan &plan, float *lut, cudaStream_t st);

@@ -112,7 +112,7 @@ struct vaqgpu_index {
   bool timed = false;
   int32_t cfg[12] = {};
 
-  DevBuf w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
+  DevBuf w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
 };
 
 struct hamgpu_index {
@@ -305,6 +305,71 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   ScanLayout lay;
   LutPlan plan;
   int32_t res_floats = 0, spill_floats = 0;
+
+  // ---- fp16 lower-bound tables, query tiles of 8 (default when eight queries' tables fit) -------------
+  bool filter16 = filter && !(flags & VAQGPU_SCAN_F32) && nq >= tune_knob("min16", 5);
+  if (filter16) {
+    apply_residency(h, (size_t)1 << 30, 8, lay, plan, res_floats, spill_floats);      // everything resident
+    if (adc_filter16_smem_bytes(plan.row_stride, k, 1024) > kSmemCap) filter16 = false;
+  }
+  if (filter16) {
+    const int T = 8, threads = tune_knob("threads", 1024);
+    const size_t smem = adc_filter16_smem_bytes(plan.row_stride, k, threads);
+    const int nwarps = threads / 32;
+    const size_t bytes_per_q = (size_t)plan.row_stride * 4;
+    int qb_max = (int)std::max<size_t>(T, std::min<size_t>((size_t)nq, kLutWorkspaceBytes / bytes_per_q));
+    qb_max = (qb_max + T - 1) / T * T;
+    const int qtiles_first = (std::min(nq, qb_max) + T - 1) / T;
+    const int64_t target = (int64_t)h->num_sms * 3;
+    int64_t n_chunks = std::max<int64_t>(1, (target + qtiles_first - 1) / qtiles_first);
+    n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16)));
+    n_chunks = std::max<int64_t>(n_chunks, (n_tiles + 32767) / 32768);          // <= 1M rows per chunk
+    n_chunks = tune_knob("chunks", (int)n_chunks);
+    const int64_t chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
+    n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+    if (n_chunks > 65535) return fail(VAQGPU_EINVAL, "index too large for one launch (%lld chunks)", (long long)n_chunks);
+    const int out_slots = (int)n_chunks;
+
+    CU(h->w_lut.ensure((size_t)qb_max * bytes_per_q));
+    CU(h->w_lut16.ensure((size_t)qb_max * bytes_per_q / 2));
+    CU(h->w_scale.ensure((size_t)qb_max * sizeof(float)));
+    CU(h->w_keys.ensure((size_t)qb_max * out_slots * k * sizeof(uint64_t)));
+    CU(h->w_thr.ensure((size_t)qb_max * sizeof(uint32_t)));
+    if (out_slots > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((out_slots + 15) / 16) * k * sizeof(uint64_t)));
+
+    for (int q0 = 0; q0 < nq; q0 += qb_max) {
+      const int qb = std::min(qb_max, nq - q0);
+      const int qb_pad = (qb + T - 1) / T * T;
+      const float *qp = d_qproj + (size_t)q0 * h->D;
+      CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, plan, (float *)h->w_lut.p, st));
+      CU(launch_lut16_build((const float *)h->w_lut.p, qb_pad / T, plan.row_stride, plan.total_entries, h->w_lut16.p,
+                            (float *)h->w_scale.p, st));
+      CU(launch_fill_u32((uint32_t *)h->w_thr.p, qb, 0xFFFFFFFFu, st));
+      launches += 3;
+      if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
+      AdcFilter16Args a{};
+      a.codes = h->d_codes; a.n_rows = h->n_rows;
+      a.lut16 = h->w_lut16.p; a.lut32 = (const float *)h->w_lut.p; a.scale = (const float *)h->w_scale.p;
+      a.lut_stride = plan.row_stride;
+      a.nq = qb; a.k = k; a.out_slots = out_slots; a.slot_base = 0;
+      a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles;
+      a.out_keys = (uint64_t *)h->w_keys.p;
+      a.thr_global = (uint32_t *)h->w_thr.p;
+      a.lay = lay;
+      CU(launch_adc_filter16_scan(a, threads, smem, st));
+      launches++;
+      if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
+      CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)out_slots * k, out_slots, qb, k, want_sqrt ? 1 : 0, 0,
+                           d_labels ? d_labels + (size_t)q0 * k : nullptr, d_dists ? (void *)(d_dists + (size_t)q0 * k) : nullptr,
+                           d_keys ? d_keys + (size_t)q0 * k : nullptr, nullptr, h->id_base, (uint64_t *)h->w_scratch.p, st));
+      launches += out_slots > 16 ? 2 : 1;
+    }
+    if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
+    h->cfg[0] = threads; h->cfg[1] = (int32_t)n_chunks; h->cfg[2] = res_floats; h->cfg[3] = 0;
+    h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
+    h->cfg[8] = T; h->cfg[9] = 3; h->cfg[10] = 0;
+    return VAQGPU_OK;
+  }
 
   if (filter) {
     // ---- query-tile width T and residency -------------------------------------------------------
@@ -520,7 +585,7 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   cudaFree(h->d_centroids); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
   cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size);
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
-  for (DevBuf *b : {&h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
+  for (DevBuf *b : {&h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
                     &h->w_labels, &h->w_dists, &h->w_outkeys, &h->w_cdf, &h->w_x})
     b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);

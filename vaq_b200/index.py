@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import EA, HEAP, PROJECTED, SCAN_V1, SQRT, TI, ModelDesc, check  # noqa: F401 (re-exported)
+from ._lib import EA, HEAP, PROJECTED, SCAN_F32, SCAN_V1, SQRT, TI, ModelDesc, check  # noqa: F401 (re-exported)
 
 
 def _c(a, dtype):
