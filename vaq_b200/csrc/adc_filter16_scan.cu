@@ -38,13 +38,19 @@ constexpr float kMargin = 1.0f + 1.0f / 512.0f;
 
 __device__ __forceinline__ uint32_t half_bits_ru(float x) { return (uint32_t)__half_as_ushort(__float2half_ru(x)); }
 
-__device__ __forceinline__ uint4 lds128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
-
-__device__ __forceinline__ uint4 lds128_volatile(const void *p) {
+// shared-memory loads by 32-bit shared address (keeps the generic->shared window arithmetic out of the loop)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 r;
-  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
+__device__ __forceinline__ uint4 lds128_volatile(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+// four 0xFF/0x00 flag bytes -> 4-bit mask (bit i = byte i set)
+__device__ __forceinline__ uint32_t bytes_to_nibble(uint32_t b) { return ((b & 0x01010101u) * 0x10204080u) >> 28; }
 
 __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
 
@@ -124,9 +130,17 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
 
   int64_t tl = tile_begin + warp;
   uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-  if (tl < tile_end) cur = ldg_stream_u4(a.codes + ((size_t)tl * W) * kTileRows + lane);
-  if (tl + nwarps < tile_end) nxt = ldg_stream_u4(a.codes + ((size_t)(tl + nwarps) * W) * kTileRows + lane);
+  const uint4 *pnext = a.codes + ((size_t)(tl + nwarps) * W) * kTileRows + lane;     // tile whose words `nxt` holds
+  const size_t pstep = (size_t)nwarps * W * kTileRows;
+  if (tl < tile_end) cur = ldg_stream_u4(pnext - pstep);
+  if (tl + nwarps < tile_end) nxt = ldg_stream_u4(pnext);
   int refresh = 0;
+  const uint32_t rows_here = (uint32_t)(min(a.n_rows, tile_end << 5) - row_base);    // valid rows of this chunk
+  const uint32_t s_base = smem_u32(smem_raw);
+  const uint32_t s_thr_h = smem_u32(thr_h);
+  uint32_t s1_addr[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) s1_addr[i] = s_base + s1_off[i];
 
   while (true) {
     const bool more = tl < tile_end;
@@ -213,7 +227,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
               c = __shfl_sync(0xffffffffu, c, 0);      // one observer: the decision must be warp-uniform
               if (!(kk < c)) continue;
             }
-            if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) __nanosleep(20);
+            if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) __nanosleep(200);
             __syncwarp();
             const uint64_t before = lst[k - 1];
             const uint64_t kth = warp_list_insert(lst, k, kk, lane);
@@ -237,10 +251,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     // ---- stage 1 on one tile ---------------------------------------------------------------------------
     const uint4 w0 = cur;
     cur = nxt;
-    {
-      const int64_t tn = tl + 2 * (int64_t)nwarps;
-      if (tn < tile_end) nxt = ldg_stream_u4(a.codes + ((size_t)tn * W) * kTileRows + lane);
-    }
+    pnext += pstep;
+    if (tl + 2 * (int64_t)nwarps < tile_end) nxt = ldg_stream_u4(pnext);
     if (((++refresh) & 31) == 0 && lane < T8 && q0 + lane < a.nq) {
       // pick up bounds published by other row chunks of this query tile
       const uint32_t g = *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane);
@@ -249,16 +261,14 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
         atomicMin(thr_h + lane, half_bits_ru(__uint_as_float(g) * scale_m[lane]));
       }
     }
-    const uint4 th0 = lds128_volatile(thr_h), th1 = lds128_volatile(thr_h + 4);
-    const __half2 thr2[4] = {as_h2(__byte_perm(th0.x, th0.y, 0x5410)), as_h2(__byte_perm(th0.z, th0.w, 0x5410)),
-                             as_h2(__byte_perm(th1.x, th1.y, 0x5410)), as_h2(__byte_perm(th1.z, th1.w, 0x5410))};
+    const uint4 th0 = lds128_volatile(s_thr_h), th1 = lds128_volatile(s_thr_h + 16);
     __half2 acc[4];
 #pragma unroll
     for (int i1 = 0; i1 < 4; i1++) {
       if (i1 < G1) {
         const uint32_t lo = s1_hi[i1] ? w0.y : w0.x, hi = s1_hi[i1] ? w0.z : w0.y;
         const uint32_t code = __funnelshift_r(lo, hi, s1_sh[i1]) & s1_mask[i1];
-        const uint4 v = lds128(smem_raw + s1_off[i1] + code * (T8 * 2));
+        const uint4 v = lds128(s1_addr[i1] + code * (T8 * 2));
         if (i1 == 0) { acc[0] = as_h2(v.x); acc[1] = as_h2(v.y); acc[2] = as_h2(v.z); acc[3] = as_h2(v.w); }
         else {
           acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
@@ -266,22 +276,30 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
         }
       }
     }
-    const int64_t row = (tl << 5) + lane;
-    unsigned sb = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const unsigned alive = ~__hgt2_mask(acc[j], thr2[j]);      // 0xFFFF per half that is NOT above its bound
-      sb |= ((alive & 1u) | ((alive >> 15) & 2u)) << (2 * j);
-    }
-    sb = (row < a.n_rows) ? (sb & qmask) : 0u;
+    // per query: is the partial lower bound above the bound?  (0xFFFF per half that is)
+    const uint32_t m0 = __hgt2_mask(acc[0], as_h2(__byte_perm(th0.x, th0.y, 0x5410)));
+    const uint32_t m1 = __hgt2_mask(acc[1], as_h2(__byte_perm(th0.z, th0.w, 0x5410)));
+    const uint32_t m2 = __hgt2_mask(acc[2], as_h2(__byte_perm(th1.x, th1.y, 0x5410)));
+    const uint32_t m3 = __hgt2_mask(acc[3], as_h2(__byte_perm(th1.z, th1.w, 0x5410)));
+    const uint32_t dead = bytes_to_nibble(__byte_perm(m0, m1, 0x6420)) | (bytes_to_nibble(__byte_perm(m2, m3, 0x6420)) << 4);
+    const uint32_t rel = ((uint32_t)(tl - tile_begin) << 5) + lane;
+    unsigned sb = (rel < rows_here) ? (~dead & qmask) : 0u;
     if (__any_sync(0xffffffffu, sb != 0)) {
-      const uint32_t rel = (uint32_t)(row - row_base) << 3;
+      // compact the surviving (row, query) pairs into the warp's queue: exclusive scan of the per-lane counts
+      const int cnt = __popc(sb);
+      int incl = cnt;
 #pragma unroll
-      for (int t = 0; t < T8; t++) {
-        const unsigned m = __ballot_sync(0xffffffffu, (sb >> t) & 1u);
-        if ((sb >> t) & 1u) q1[q1n + __popc(m & lt_mask)] = rel | (uint32_t)t;
-        q1n += __popc(m);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
+      int pos = q1n + incl - cnt;
+      while (sb) {
+        const int t = __ffs(sb) - 1;
+        sb &= sb - 1;
+        q1[pos++] = (rel << 3) | (uint32_t)t;
+      }
+      q1n += __shfl_sync(0xffffffffu, incl, 31);
     }
     tl += nwarps;
   }
