@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t hamming_words(const uint4 (&r)[W], const uin
 }
 
 template <int W, int QT>
-__global__ void ham_scan_kernel(const __grid_constant__ HamScanArgs a) {
+__global__ void __launch_bounds__(256, (W <= 2 ? 4 : 2)) ham_scan_kernel(const __grid_constant__ HamScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int k = a.k;
@@ -84,22 +84,34 @@ __global__ void ham_scan_kernel(const __grid_constant__ HamScanArgs a) {
     for (int j = 0; j < W; j++) dst[j] = ldg_stream_u4(p + j * kTileRows);
   };
   if (t < n_tiles) load(cur, t);
-  for (; t < n_tiles; t += gstride) {
+  // distance part of each query's running k-th key, kept in registers: the per-row test is one compare;
+  // the exact (distance, row) key test and the list update only run for rows that pass it
+  uint32_t thr_d[QT];
+#pragma unroll
+  for (int qi = 0; qi < QT; qi++) thr_d[qi] = 0xFFFFFFFFu;
+  int iter = 0;
+  for (; t < n_tiles; t += gstride, iter++) {
     const int tn = t + gstride;
     if (tn < n_tiles) load(nxt, tn);
     const int row = t * kTileRows + lane;
     const bool valid = row < a.n_rows;
+    if ((iter & 15) == 15) {
+      // adopt tighter bounds other warps of the CTA have reached
+#pragma unroll
+      for (int qi = 0; qi < QT; qi++)
+        thr_d[qi] = min(thr_d[qi], (uint32_t)(*reinterpret_cast<volatile uint64_t *>(blk_thr + qi) >> 32));
+    }
 #pragma unroll
     for (int qi = 0; qi < QT; qi++) {
       if (qi < nqt) {
         const uint32_t d = hamming_words<W>(cur, sq + qi * W);
-        volatile uint64_t *mylist = lists + ((size_t)warp * QT + qi) * k;
-        uint64_t thrkey = mylist[k - 1];
-        const uint64_t bthr = *reinterpret_cast<volatile uint64_t *>(blk_thr + qi);
-        thrkey = bthr < thrkey ? bthr : thrkey;
-        const uint64_t key = valid ? (((uint64_t)d << 32) | (uint32_t)row) : kEmptyKey;
-        unsigned m = __ballot_sync(0xffffffffu, key < thrkey);
-        if (m) {
+        if (__any_sync(0xffffffffu, d <= thr_d[qi])) {
+          volatile uint64_t *mylist = lists + ((size_t)warp * QT + qi) * k;
+          uint64_t thrkey = mylist[k - 1];
+          const uint64_t bthr = *reinterpret_cast<volatile uint64_t *>(blk_thr + qi);
+          thrkey = bthr < thrkey ? bthr : thrkey;
+          const uint64_t key = valid ? (((uint64_t)d << 32) | (uint32_t)row) : kEmptyKey;
+          unsigned m = __ballot_sync(0xffffffffu, key < thrkey);
           uint64_t kth = thrkey;
           while (m) {
             const int src = __ffs(m) - 1;
@@ -107,8 +119,8 @@ __global__ void ham_scan_kernel(const __grid_constant__ HamScanArgs a) {
             const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
             kth = warp_list_insert(mylist, k, kk, lane);
           }
-          if (lane == 0 && kth != kEmptyKey)
-            atomicMin(reinterpret_cast<unsigned long long *>(blk_thr + qi), (unsigned long long)kth);
+          if (kth < thrkey && lane == 0) atomicMin(reinterpret_cast<unsigned long long *>(blk_thr + qi), (unsigned long long)kth);
+          thr_d[qi] = (uint32_t)(kth >> 32);
         }
       }
     }
