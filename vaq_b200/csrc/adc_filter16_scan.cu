@@ -179,6 +179,29 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
       const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
       float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
       if (!exact) thr *= scale_m[t];
+      // Rows of up to 256 bits are fetched once (W 16-byte loads per lane) and walked from registers: the
+      // fields come in increasing bit order, so a two-word window (lo, hi) slides over the eight words and a
+      // word is picked by a select tree on the (warp-uniform) word index.  A 4-byte load per field would
+      // cost 32 L1 wavefronts each (every lane has a different row).
+      uint32_t wd[8];
+      if constexpr (W <= 2) {
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(rp));
+        wd[0] = v0.x; wd[1] = v0.y; wd[2] = v0.z; wd[3] = v0.w;
+        if constexpr (W == 2) {
+          const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(rp) + kTileRows);
+          wd[4] = v1.x; wd[5] = v1.y; wd[6] = v1.z; wd[7] = v1.w;
+        } else {
+          wd[4] = wd[5] = wd[6] = wd[7] = 0u;
+        }
+      }
+      auto selw = [&](int i) -> uint32_t {
+        const uint32_t s0 = (i & 1) ? wd[1] : wd[0], s1 = (i & 1) ? wd[3] : wd[2];
+        const uint32_t s2 = (i & 1) ? wd[5] : wd[4], s3 = (i & 1) ? wd[7] : wd[6];
+        const uint32_t t0 = (i & 2) ? s1 : s0, t1 = (i & 2) ? s3 : s2;
+        return (i & 8) ? 0u : ((i & 4) ? t1 : t0);
+      };
+      int widx = -2;
+      uint32_t lo = 0u, hi = 0u;
       bool alive = true;
       for (int g = fb; g < fe; g += 4) {
         float dism = 0.f;
@@ -187,7 +210,17 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
           const int f = g + j;
           if (f < fe) {
             const uint32_t meta = a.lay.fmeta[f];
-            const uint32_t lo = __ldg(rp + a.lay.fw_lo[f]), hi = __ldg(rp + a.lay.fw_hi[f]);
+            if constexpr (W <= 2) {
+              const int fw = a.lay.fword[f];
+              if (fw != widx) {
+                lo = (fw == widx + 1) ? hi : selw(fw);
+                hi = selw(fw + 1);
+                widx = fw;
+              }
+            } else {
+              lo = __ldg(rp + a.lay.fw_lo[f]);
+              hi = __ldg(rp + a.lay.fw_hi[f]);
+            }
             const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
             const uint32_t idx = (a.lay.foff[f] + code) * T8 + t;
             dism += exact ? __ldg(g32 + idx) : __half2float(slut[idx]);
