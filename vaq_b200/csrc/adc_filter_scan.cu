@@ -85,13 +85,34 @@ __device__ __forceinline__ void lds_thr(float (&out)[T], const uint32_t *p) {
 
 // Exact score of one (row, query) pair per lane over the fields [f_begin, f_end) (f_begin a multiple of
 // 4), continuing from `dist`, in the reference's order and grouping (dism = ((l0+l1)+l2)+l3 ;
-// dist += dism, VAQ.cpp:1741-1748).  The row's 32-bit words are fetched through L1 as the walk needs
-// them (each lane has a different row, so there is nothing to coalesce; a compact loop keeps the kernel
-// inside the instruction cache).  Returns false when every lane abandoned.
-template <int T>
+// dist += dism, VAQ.cpp:1741-1748).  A compact loop (no per-word unrolling) keeps the kernel inside the
+// instruction cache.  Returns false when every lane abandoned.
+template <int W, int T>
 __device__ __forceinline__ bool score_fields(const uint32_t *__restrict__ rp, const ScanLayout &lay, const float *__restrict__ slut,
                                              const float *__restrict__ gspill, int t, float thr, bool active, int f_begin,
                                              int f_end, float &dist) {
+  // Rows of up to 256 bits are fetched once (W 16-byte loads per lane) and walked from registers: fields come
+  // in increasing bit order, so a two-word window slides over the eight words and a word is picked by a select
+  // tree on the warp-uniform word index (a 4-byte load per field costs 32 L1 wavefronts: every lane has its own row).
+  uint32_t wd[8];
+  if constexpr (W <= 2) {
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(rp));
+    wd[0] = v0.x; wd[1] = v0.y; wd[2] = v0.z; wd[3] = v0.w;
+    if constexpr (W == 2) {
+      const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(rp) + kTileRows);
+      wd[4] = v1.x; wd[5] = v1.y; wd[6] = v1.z; wd[7] = v1.w;
+    } else {
+      wd[4] = wd[5] = wd[6] = wd[7] = 0u;
+    }
+  }
+  auto selw = [&](int i) -> uint32_t {
+    const uint32_t s0 = (i & 1) ? wd[1] : wd[0], s1 = (i & 1) ? wd[3] : wd[2];
+    const uint32_t s2 = (i & 1) ? wd[5] : wd[4], s3 = (i & 1) ? wd[7] : wd[6];
+    const uint32_t t0 = (i & 2) ? s1 : s0, t1 = (i & 2) ? s3 : s2;
+    return (i & 8) ? 0u : ((i & 4) ? t1 : t0);
+  };
+  int widx = -2;
+  uint32_t lo = 0u, hi = 0u;
   for (int g = f_begin; g < f_end; g += 4) {
     float dism = 0.f;
 #pragma unroll
@@ -99,7 +120,17 @@ __device__ __forceinline__ bool score_fields(const uint32_t *__restrict__ rp, co
       const int f = g + j;
       if (f < f_end) {
         const uint32_t meta = lay.fmeta[f];
-        const uint32_t lo = __ldg(rp + lay.fw_lo[f]), hi = __ldg(rp + lay.fw_hi[f]);
+        if constexpr (W <= 2) {
+          const int fw = lay.fword[f];
+          if (fw != widx) {
+            lo = (fw == widx + 1) ? hi : selw(fw);
+            hi = selw(fw + 1);
+            widx = fw;
+          }
+        } else {
+          lo = __ldg(rp + lay.fw_lo[f]);
+          hi = __ldg(rp + lay.fw_hi[f]);
+        }
         const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
         const uint32_t idx = (lay.foff[f] + code) * T + t;
         const float v = (meta & kFieldSpill) ? __ldg(gspill + idx) : slut[idx];
@@ -340,7 +371,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
       const int64_t row = row_base + (e >> 3);
       const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
       const float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
-      if (score_fields<T>(rp, a.lay, slut, gspill, t, thr, active, fb, fe, dist)) {
+      if (score_fields<W, T>(rp, a.lay, slut, gspill, t, thr, active, fb, fe, dist)) {
         if (level == 1 && two_level) {
           const bool s = active && !(dist > thr);
           const unsigned m = __ballot_sync(0xffffffffu, s);
