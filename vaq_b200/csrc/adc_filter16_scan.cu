@@ -56,7 +56,9 @@ __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<
 
 }  // namespace
 
-template <int W>
+// FAST1: the first group has four fields that all start in the row's first 32-bit word (e.g. four 9- or
+// 10-bit subspaces) — stage 1 then needs no per-field word selection and no group-size checks.
+template <int W, bool FAST1>
 __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid_constant__ AdcFilter16Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -84,7 +86,9 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     const uint32_t g = a.thr_global[q];
     scale_m[tid] = sm;
     thr_f[tid] = g;
-    thr_h[tid] = half_bits_ru(__uint_as_float(g) * sm);
+    // queries past nq (padding of the last tile) get the bound -1.0: every lower bound is above it, so they
+    // never survive stage 1 and nothing ever updates the slot
+    thr_h[tid] = (q0 + tid < a.nq) ? half_bits_ru(__uint_as_float(g) * sm) : 0xBC00u;
     locks[tid] = 0u;
   }
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -115,7 +119,6 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   const bool two_level = M > 8;
   const int F2 = two_level ? 8 : M;
 
-  const unsigned qmask = (a.nq - q0 >= T8) ? 0xFFu : ((1u << (a.nq - q0)) - 1u);
   uint32_t *q1 = queues + (size_t)warp * (kQ1Cap16 + 3 * kQCap);
   uint32_t *q2e = q1 + kQ1Cap16;
   float *q2d = reinterpret_cast<float *>(q2e + kQCap);
@@ -145,14 +148,16 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   while (true) {
     const bool more = tl < tile_end;
     int level = 0, take = 0;
-    if (q3n >= 32) { level = 3; take = 32; }
-    else if (q2n >= 32) { level = 2; take = 32; }
-    else if (q1n >= 32) { level = 1; take = 32; }
-    else if (!more) {
-      if (q1n > 0) { level = 1; take = q1n; }
-      else if (q2n > 0) { level = 2; take = q2n; }
-      else if (q3n > 0) { level = 3; take = q3n; }
-      else break;
+    if (((q1n | q2n | q3n) >= 32) || !more) {           // rarely true: keep the common path to one test
+      if (q3n >= 32) { level = 3; take = 32; }
+      else if (q2n >= 32) { level = 2; take = 32; }
+      else if (q1n >= 32) { level = 1; take = 32; }
+      else if (!more) {
+        if (q1n > 0) { level = 1; take = q1n; }
+        else if (q2n > 0) { level = 2; take = q2n; }
+        else if (q3n > 0) { level = 3; take = q3n; }
+        else break;
+      }
     }
     if (level) {
       // ---- survivors: one code site for the two lower-bound levels and the exact level ----------------
@@ -298,8 +303,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     __half2 acc[4];
 #pragma unroll
     for (int i1 = 0; i1 < 4; i1++) {
-      if (i1 < G1) {
-        const uint32_t lo = s1_hi[i1] ? w0.y : w0.x, hi = s1_hi[i1] ? w0.z : w0.y;
+      if (FAST1 || i1 < G1) {
+        const uint32_t lo = (!FAST1 && s1_hi[i1]) ? w0.y : w0.x, hi = (!FAST1 && s1_hi[i1]) ? w0.z : w0.y;
         const uint32_t code = __funnelshift_r(lo, hi, s1_sh[i1]) & s1_mask[i1];
         const uint4 v = lds128(s1_addr[i1] + code * (T8 * 2));
         if (i1 == 0) { acc[0] = as_h2(v.x); acc[1] = as_h2(v.y); acc[2] = as_h2(v.z); acc[3] = as_h2(v.w); }
@@ -316,7 +321,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     const uint32_t m3 = __hgt2_mask(acc[3], as_h2(__byte_perm(th1.z, th1.w, 0x5410)));
     const uint32_t dead = bytes_to_nibble(__byte_perm(m0, m1, 0x6420)) | (bytes_to_nibble(__byte_perm(m2, m3, 0x6420)) << 4);
     const uint32_t rel = ((uint32_t)(tl - tile_begin) << 5) + lane;
-    unsigned sb = (rel < rows_here) ? (~dead & qmask) : 0u;
+    unsigned sb = ~dead & 0xFFu;
+    if (tl == tile_end - 1 && rel >= rows_here) sb = 0u;      // only the last tile of the index can be partial
     if (__any_sync(0xffffffffu, sb != 0)) {
       // compact the surviving (row, query) pairs into the warp's queue: exclusive scan of the per-lane counts
       const int cnt = __popc(sb);
@@ -354,19 +360,26 @@ size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads) {
   return b;
 }
 
-template <int W>
-static cudaError_t launch16_w(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
+template <int W, bool FAST1>
+static cudaError_t launch16_wf(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
   static size_t configured = 0;
   if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(adc_filter16_scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(adc_filter16_scan_kernel<W, FAST1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     configured = smem_bytes;
   }
   const int64_t nt = a.tile_hi - a.tile_lo;
   if (nt <= 0) return cudaSuccess;
   dim3 grid((unsigned)((a.nq + T8 - 1) / T8), (unsigned)((nt + a.chunk_tiles - 1) / a.chunk_tiles));
-  adc_filter16_scan_kernel<W><<<grid, threads, smem_bytes, st>>>(a);
+  adc_filter16_scan_kernel<W, FAST1><<<grid, threads, smem_bytes, st>>>(a);
   return cudaGetLastError();
+}
+
+template <int W>
+static cudaError_t launch16_w(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
+  bool fast1 = a.lay.M >= 4;
+  for (int f = 0; f < 4 && fast1; f++) fast1 = a.lay.fword[f] == 0;
+  return fast1 ? launch16_wf<W, true>(a, threads, smem_bytes, st) : launch16_wf<W, false>(a, threads, smem_bytes, st);
 }
 
 cudaError_t launch_adc_filter16_scan(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
