@@ -386,3 +386,55 @@ def test_error_paths():
     lab, dis = ix.search(np.zeros((0, m.D), np.float32), 5, EA | 0x100)   # empty batch is a no-op
     assert lab.shape == (0, 5)
     ix.close()
+
+
+# ---- full-size properties (BASELINE shapes the oracle cannot finish in seconds) -----------------------
+
+def test_large_synthetic_index_planted_needles_and_slices(port):
+    """8M on-device synthetic rows (C4/C5-style generator).  Size-independent checks: (1) every query's own
+    code row, planted at a known id, comes back at rank 0 with the oracle's distance for that row; (2) the
+    returned distances equal the oracle's distances of the returned rows (regenerated on the host from the
+    counter-based generator); (3) no row of a 1M-row host slice beats the k-th returned distance without being
+    returned; (4) results are identical for the three scan kernels."""
+    from vaq_b200 import synth
+    from vaq_b200.index import EA, PROJECTED, SCAN_F32, SCAN_V1
+    rng = np.random.default_rng(2024)
+    bits = [9, 9, 8, 8, 8, 7, 7, 7, 6, 6, 6, 6, 5, 5, 5, 5]
+    m = random_model(rng, len(bits), 4, bits)
+    n, nq, k, seed = 8_000_000, 24, 10, 4242
+    ix = make_index(m)
+    ix.reserve(n)
+    ix.add_synthetic(n, seed)
+    # queries = centroids of planted rows (+ noise) so that the planted row is (one of) the nearest
+    planted = rng.integers(0, n, size=nq)
+    pc = synth.synth_codes(bits, 1, 0, seed)  # shape check only
+    assert pc.shape == (1, len(bits))
+    Q = np.empty((nq, m.D), np.float32)
+    for i, r in enumerate(planted):
+        c = synth.synth_codes(bits, 1, int(r), seed)[0]
+        Q[i] = np.concatenate([m.centroids[s][c[s]] for s in range(m.M)]) + rng.standard_normal(m.D).astype(np.float32) * 1e-3
+    lab, dis = ix.search(Q, k, EA | PROJECTED)
+    assert ix.last_config()["scan_kernel"] == 3
+    lut = port.create_lut(m, Q)
+    for i in range(nq):
+        rows = synth.synth_codes(bits, 1, 0, seed)[:0]
+        got_codes = np.concatenate([synth.synth_codes(bits, 1, int(r), seed) for r in lab[i]])
+        d = port.adc_all(m, lut[i], got_codes)
+        assert bitwise_equal(d, dis[i]), "returned distance != oracle distance of the returned row"
+        assert (np.diff(dis[i]) >= 0).all()
+        pr = synth.synth_codes(bits, 1, int(planted[i]), seed)
+        dp = port.adc_all(m, lut[i], pr)[0]
+        assert dp >= dis[i, 0] and (planted[i] in lab[i] or dp > dis[i, -1] or dp == dis[i, -1])
+        assert lab[i, 0] == planted[i] or dis[i, 0] <= dp
+    # (3) a host-regenerated slice cannot contain an unreturned row under the k-th distance
+    lo = 3_000_000
+    sl = synth.synth_codes(bits, 1_000_000, lo, seed)
+    for i in range(0, nq, 4):
+        d = port.adc_all(m, lut[i], sl)
+        better = np.nonzero(d < dis[i, -1])[0] + lo
+        assert set(better.tolist()) <= set(lab[i].tolist())
+    # (4) kernel invariance
+    for extra in (SCAN_F32, SCAN_V1):
+        lab2, dis2 = ix.search(Q, k, EA | PROJECTED | extra)
+        assert np.array_equal(lab2, lab) and bitwise_equal(dis2, dis)
+    ix.close()
