@@ -5,6 +5,7 @@
 // Same structure as adc_filter_scan.cu (stage 1 over every (row, query) pair on the first group of
 // subspaces, compacted survivors scored by full-lane warps), but the shared-memory tables hold
 //     e16[s][c][t] = round_toward_zero_fp16( scale_t * lut[t][s][c] ),     t = 0..7 (query tile of 8)
+// (written by lut_build_kernel<8> together with the fp32 tables; scale_t is a per-query power of two)
 // i.e. guaranteed LOWER bounds of the reference's table entries, 16 bytes per code for 8 queries.  One
 // LDS.128 therefore serves eight queries (the fp32 form serves four), which halves both the shared-memory
 // wavefronts and the instructions per pair — the two resources the fp32 form saturates (ncu: LSU 86 %,
@@ -394,68 +395,6 @@ cudaError_t launch_adc_filter16_scan(const AdcFilter16Args &a, int threads, size
     case 8: return launch16_w<8>(a, threads, smem_bytes, st);
     default: return cudaErrorInvalidValue;
   }
-}
-
-// ---- fp16 lower-bound tables ------------------------------------------------------------------------
-// One CTA per query tile: per-query maximum over the tile's fp32 tables -> power-of-two scale that puts
-// the largest entry in (8000, 16000] (four of them still sum below the fp16 maximum), then
-// e16 = round_toward_zero(scale * entry).  Entries past `n_entries` (alignment padding) become 0.
-__global__ void __launch_bounds__(256) lut16_build_kernel(const float *__restrict__ lut32, int lut_stride, int n_entries,
-                                                          __half *__restrict__ lut16, float *__restrict__ scale) {
-  __shared__ float smax[8][T8];
-  __shared__ float sscale[T8];
-  const int qt = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float4 *src = reinterpret_cast<const float4 *>(lut32 + (size_t)qt * lut_stride * T8);
-  float m[T8];
-#pragma unroll
-  for (int t = 0; t < T8; t++) m[t] = 0.f;
-  for (int e = tid; e < n_entries; e += blockDim.x) {
-    const float4 a = __ldg(src + 2 * e), b = __ldg(src + 2 * e + 1);
-    m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
-    m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
-  }
-#pragma unroll
-  for (int t = 0; t < T8; t++) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m[t] = fmaxf(m[t], __shfl_xor_sync(0xffffffffu, m[t], o));
-    if (lane == 0) smax[warp][t] = m[t];
-  }
-  __syncthreads();
-  if (tid < T8) {
-    float mx = 0.f;
-    for (int w = 0; w < 8; w++) mx = fmaxf(mx, smax[w][tid]);
-    float s = 1.f;
-    if (mx > 0.f && mx < 3.0e38f) {
-      int ex = (int)floorf(log2f(16000.f / mx));
-      ex = max(-100, min(100, ex));
-      s = exp2f((float)ex);
-      while (mx * s > 16000.f) s *= 0.5f;       // guard against log2f rounding at the boundary
-    }
-    sscale[tid] = s;
-    scale[qt * T8 + tid] = s;
-  }
-  __syncthreads();
-  uint4 *dst = reinterpret_cast<uint4 *>(lut16 + (size_t)qt * lut_stride * T8);
-  for (int e = tid; e < lut_stride; e += blockDim.x) {
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (e < n_entries) {
-      const float4 a = __ldg(src + 2 * e), b = __ldg(src + 2 * e + 1);
-      const __half2 h0 = __halves2half2(__float2half_rz(a.x * sscale[0]), __float2half_rz(a.y * sscale[1]));
-      const __half2 h1 = __halves2half2(__float2half_rz(a.z * sscale[2]), __float2half_rz(a.w * sscale[3]));
-      const __half2 h2 = __halves2half2(__float2half_rz(b.x * sscale[4]), __float2half_rz(b.y * sscale[5]));
-      const __half2 h3 = __halves2half2(__float2half_rz(b.z * sscale[6]), __float2half_rz(b.w * sscale[7]));
-      o = make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
-                     *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
-    }
-    dst[e] = o;
-  }
-}
-
-cudaError_t launch_lut16_build(const float *lut32, int n_qtiles, int lut_stride, int n_entries, void *lut16, float *scale,
-                               cudaStream_t st) {
-  if (n_qtiles <= 0) return cudaSuccess;
-  lut16_build_kernel<<<n_qtiles, 256, 0, st>>>(lut32, lut_stride, n_entries, reinterpret_cast<__half *>(lut16), scale);
-  return cudaGetLastError();
 }
 
 }  // namespace vaqgpu

@@ -209,12 +209,11 @@ struct AdcFilter16Args {
 };
 size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads);
 cudaError_t launch_adc_filter16_scan(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st);
-cudaError_t launch_lut16_build(const float *lut32, int n_qtiles, int lut_stride, int n_entries, void *lut16, float *scale,
-                               cudaStream_t st);
 
-// nq_launch >= nq queries are written (tile padding repeats the last query)
-cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, const float *centroids,
-                             const LutPlan &plan, float *lut, cudaStream_t st);
+// nq_launch >= nq query slots are written (tile padding repeats the last query).  With plan.T == 8 and
+// lut16 != NULL the fp16 lower-bound tables and the per-query scales are written by the same kernel.
+cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, const float *centroids, const float *cent_rmax,
+                             const LutPlan &plan, float *lut, void *lut16, float *scale, cudaStream_t st);
 cudaError_t launch_project(const float *x, int n, int D, const float *eig, float *out, cudaStream_t st);
 
 cudaError_t launch_pack_codes(const uint16_t *codes, int64_t n, int64_t row0, const ScanLayout &lay, uint4 *packed,

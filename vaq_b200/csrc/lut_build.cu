@@ -10,6 +10,8 @@
 // FP32 FMA only: the contraction depth is L (3..15) and the LUT must match the reference to
 // 1e-5 relative, which TF32/BF16 tensor-core inputs (~1e-3) cannot deliver; the build is < 1 %
 // of a search, so tcgen05 would buy nothing here (DESIGN.md "LUT build").
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace vaqgpu {
@@ -54,12 +56,54 @@ __device__ __forceinline__ float l2sqr_small(const float *__restrict__ x, const 
   }
 }
 
-__global__ void lut_build_kernel(const float *__restrict__ q_proj, int nq, int D, const float *__restrict__ cent,
-                                 const __grid_constant__ LutPlan p, float *__restrict__ lut) {
+// One thread per table entry and query TILE: the centroid is read once, the T queries of the tile are
+// scored against it and the T values are written as one contiguous T*4-byte store — the interleaved
+// [entry][T] layout the scan kernels read — so the stores of a warp are fully coalesced.  Optionally the
+// same thread also writes the fp16 lower-bound entries for the tile (T == 8 only):
+//     e16 = round_toward_zero(scale_t * value),   scale_t = 2^floor(log2(16000 / ub_t)),
+//     ub_t = max_s (|q_t,s| + max_c |C_s[c]|)^2  >= every entry of query t (triangle inequality),
+// so scale_t * entry <= 16000 and four entries still sum below the fp16 maximum.  fp16 keeps 11 significant
+// bits at any scale, so the looseness of ub only costs exponent range.
+template <int T>
+__global__ void __launch_bounds__(256) lut_build_kernel(const float *__restrict__ q_proj, int nq, int D, const float *__restrict__ cent,
+                                                        const float *__restrict__ cent_rmax, const __grid_constant__ LutPlan p,
+                                                        float *__restrict__ lut, __half *__restrict__ lut16,
+                                                        float *__restrict__ scale) {
+  __shared__ float sscale[T];
+  const int qt = blockIdx.y;
+  const int L = p.L;
+  if (lut16 != nullptr) {
+    if (threadIdx.x < 32) {
+      for (int t = 0; t < T; t++) {
+        const int q = min(qt * T + t, nq - 1);
+        float ub = 0.f;
+        for (int s = threadIdx.x; s < p.M; s += 32) {
+          const float *qs = q_proj + (size_t)q * D + (size_t)s * L;
+          float n2 = 0.f;
+          for (int j = 0; j < L; j++) n2 = fmaf(qs[j], qs[j], n2);
+          const float r = sqrtf(n2) + cent_rmax[s];
+          ub = fmaxf(ub, r * r);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ub = fmaxf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+        if (threadIdx.x == 0) {
+          float sc = 1.f;
+          ub *= 1.0001f;                       // the entries are computed with rounding; keep a hair of slack
+          if (ub > 0.f && ub < 3.0e38f) {
+            int ex = (int)floorf(log2f(16000.f / ub));
+            ex = max(-100, min(100, ex));
+            sc = exp2f((float)ex);
+            while (ub * sc > 16000.f) sc *= 0.5f;
+          }
+          sscale[t] = sc;
+          if (blockIdx.x == 0) scale[qt * T + t] = sc;
+        }
+      }
+    }
+    __syncthreads();
+  }
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.total_entries) return;
-  const int qo = blockIdx.y;            // output slot; slots past nq (tile padding) repeat the last query
-  const int q = min(qo, nq - 1);
   int lo = 0, hi = p.M;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -68,28 +112,60 @@ __global__ void lut_build_kernel(const float *__restrict__ q_proj, int nq, int D
   const int s = lo;
   const int c = e - p.ent_off[s];
   const int K = p.ent_off[s + 1] - p.ent_off[s];
-  const int L = p.L;
   const float *cp = cent + p.cent_off[s] + (size_t)c * L;
-  const float *qs = q_proj + (size_t)q * D + (size_t)s * L;
-  float acc;
-  if (K >= 8) {
-    acc = 0.f;
-    for (int j = 0; j < L; j++) {
-      const float d = __fsub_rn(__ldg(qs + j), __ldg(cp + j));
-      acc = __fmaf_rn(d, d, acc);
+  float acc[T];
+#pragma unroll
+  for (int t = 0; t < T; t++) {
+    const int q = min(qt * T + t, nq - 1);      // slots past nq (tile padding) repeat the last query
+    const float *qs = q_proj + (size_t)q * D + (size_t)s * L;
+    if (K >= 8) {
+      float a = 0.f;
+      for (int j = 0; j < L; j++) {
+        const float d = __fsub_rn(__ldg(qs + j), __ldg(cp + j));
+        a = __fmaf_rn(d, d, a);
+      }
+      acc[t] = a;
+    } else {
+      acc[t] = l2sqr_small(qs, cp, L);
     }
-  } else {
-    acc = l2sqr_small(qs, cp, L);
   }
-  lut[((size_t)(qo / p.T) * p.row_stride + p.pos[s] + c) * p.T + (qo % p.T)] = acc;
+  const size_t o = ((size_t)qt * p.row_stride + p.pos[s] + c) * T;
+  if constexpr (T == 1) {
+    lut[o] = acc[0];
+  } else if constexpr (T == 2) {
+    *reinterpret_cast<float2 *>(lut + o) = make_float2(acc[0], acc[1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < T / 4; i++)
+      *reinterpret_cast<float4 *>(lut + o + 4 * i) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  }
+  if constexpr (T == 8) {
+    if (lut16 != nullptr) {
+      __half2 h[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        h[i] = __halves2half2(__float2half_rz(acc[2 * i] * sscale[2 * i]), __float2half_rz(acc[2 * i + 1] * sscale[2 * i + 1]));
+      *reinterpret_cast<uint4 *>(lut16 + o) = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
+                                                        *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
+    }
+  }
 }
 
-cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, const float *centroids,
-                             const LutPlan &plan, float *lut, cudaStream_t st) {
+// nq_launch (a multiple of plan.T) >= nq query slots are written.  lut16/scale may be NULL (fp32 tables only).
+cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, const float *centroids, const float *cent_rmax,
+                             const LutPlan &plan, float *lut, void *lut16, float *scale, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   const int threads = 256;
-  dim3 grid((unsigned)((plan.total_entries + threads - 1) / threads), (unsigned)nq_launch);
-  lut_build_kernel<<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut);
+  const int T = plan.T;
+  dim3 grid((unsigned)((plan.total_entries + threads - 1) / threads), (unsigned)((nq_launch + T - 1) / T));
+  __half *l16 = reinterpret_cast<__half *>(lut16);
+  switch (T) {
+    case 1: lut_build_kernel<1><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, cent_rmax, plan, lut, nullptr, nullptr); break;
+    case 2: lut_build_kernel<2><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, cent_rmax, plan, lut, nullptr, nullptr); break;
+    case 4: lut_build_kernel<4><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, cent_rmax, plan, lut, nullptr, nullptr); break;
+    case 8: lut_build_kernel<8><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, cent_rmax, plan, lut, l16, scale); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

@@ -3,6 +3,7 @@
 // usable sm_100 device.
 #include <cuda_runtime.h>
 #include <float.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -90,6 +91,7 @@ struct vaqgpu_index {
   LutPlan plan{};
 
   float *d_centroids = nullptr;
+  float *d_cent_rmax = nullptr;   // [M] largest centroid norm per subspace (fp16 table scaling)
   float *d_eig = nullptr;
   int32_t *d_bits = nullptr, *d_ent_off = nullptr;
 
@@ -341,11 +343,10 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       const int qb = std::min(qb_max, nq - q0);
       const int qb_pad = (qb + T - 1) / T * T;
       const float *qp = d_qproj + (size_t)q0 * h->D;
-      CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, plan, (float *)h->w_lut.p, st));
-      CU(launch_lut16_build((const float *)h->w_lut.p, qb_pad / T, plan.row_stride, plan.total_entries, h->w_lut16.p,
-                            (float *)h->w_scale.p, st));
+      CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, h->d_cent_rmax, plan, (float *)h->w_lut.p, h->w_lut16.p,
+                          (float *)h->w_scale.p, st));
       CU(launch_fill_u32((uint32_t *)h->w_thr.p, qb, 0xFFFFFFFFu, st));
-      launches += 3;
+      launches += 2;
       if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
       AdcFilter16Args a{};
       a.codes = h->d_codes; a.n_rows = h->n_rows;
@@ -418,7 +419,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       const int qb = std::min(qb_max, nq - q0);
       const int qb_pad = (qb + T - 1) / T * T;
       const float *qp = d_qproj + (size_t)q0 * h->D;
-      CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, plan, (float *)h->w_lut.p, st));
+      CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, h->d_cent_rmax, plan, (float *)h->w_lut.p, nullptr, nullptr, st));
       CU(launch_fill_u32((uint32_t *)h->w_thr.p, qb, 0xFFFFFFFFu, st));
       launches += 2;
       if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
@@ -483,7 +484,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
                               (int2 *)h->w_ranges.p, (int32_t *)h->w_nranges.p, st));
       launches++;
     }
-    CU(launch_lut_build(qp, qb, qb, h->D, h->d_centroids, plan, (float *)h->w_lut.p, st));
+    CU(launch_lut_build(qp, qb, qb, h->D, h->d_centroids, h->d_cent_rmax, plan, (float *)h->w_lut.p, nullptr, nullptr, st));
     launches++;
     if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
     AdcScanArgs a{};
@@ -563,6 +564,21 @@ int vaqgpu_create(const vaqgpu_model_desc *m, int device, vaqgpu_t **out) {
   for (int s = 0; s < m->M; s++) cent_floats += ((size_t)1 << m->bits[s]) * m->L;
   CUX(cudaMalloc(&h->d_centroids, cent_floats * sizeof(float)));
   CUX(cudaMemcpy(h->d_centroids, m->centroids, cent_floats * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    std::vector<float> rmax(m->M, 0.f);
+    size_t off = 0;
+    for (int s = 0; s < m->M; s++) {
+      const size_t K = (size_t)1 << m->bits[s];
+      for (size_t c = 0; c < K; c++) {
+        double n2 = 0;
+        for (int j = 0; j < m->L; j++) { const double v = m->centroids[off + c * m->L + j]; n2 += v * v; }
+        rmax[s] = std::max(rmax[s], (float)(sqrt(n2) * 1.0001));
+      }
+      off += K * m->L;
+    }
+    CUX(cudaMalloc(&h->d_cent_rmax, m->M * sizeof(float)));
+    CUX(cudaMemcpy(h->d_cent_rmax, rmax.data(), m->M * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if (m->eig_real) {
     CUX(cudaMalloc(&h->d_eig, (size_t)m->D * m->D * sizeof(float)));
     CUX(cudaMemcpy(h->d_eig, m->eig_real, (size_t)m->D * m->D * sizeof(float), cudaMemcpyHostToDevice));
@@ -582,7 +598,7 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   if (!h) return;
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_centroids); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
+  cudaFree(h->d_centroids); cudaFree(h->d_cent_rmax); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
   cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size);
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
   for (DevBuf *b : {&h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
@@ -726,7 +742,7 @@ int vaqgpu_build_lut(vaqgpu_t *h, const float *q_proj, int32_t nq, float *lut_ou
   CU(h->w_q.ensure((size_t)nq * h->D * sizeof(float)));
   CU(h->w_lut.ensure((size_t)nq * p.row_stride * sizeof(float)));
   CU(cudaMemcpyAsync(h->w_q.p, q_proj, (size_t)nq * h->D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  CU(launch_lut_build((const float *)h->w_q.p, nq, nq, h->D, h->d_centroids, p, (float *)h->w_lut.p, h->stream));
+  CU(launch_lut_build((const float *)h->w_q.p, nq, nq, h->D, h->d_centroids, h->d_cent_rmax, p, (float *)h->w_lut.p, nullptr, nullptr, h->stream));
   CU(cudaMemcpyAsync(lut_out, h->w_lut.p, (size_t)nq * p.row_stride * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return VAQGPU_OK;
