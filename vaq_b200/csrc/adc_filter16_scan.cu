@@ -2,28 +2,34 @@
 // VAQ::searchEarlyAbandon (reference bitvecengine/VAQ.cpp:1694-1727) when eight queries' tables fit in
 // shared memory as fp16.
 //
-// Same structure as adc_filter_scan.cu (stage 1 over every (row, query) pair on the first group of
-// subspaces, compacted survivors scored by full-lane warps), but the shared-memory tables hold
-//     e16[s][c][t] = round_toward_zero_fp16( scale_t * lut[t][s][c] ),     t = 0..7 (query tile of 8)
-// (written by lut_build_kernel<8> together with the fp32 tables; scale_t is a per-query power of two)
-// i.e. guaranteed LOWER bounds of the reference's table entries, 16 bytes per code for 8 queries.  One
-// LDS.128 therefore serves eight queries (the fp32 form serves four), which halves both the shared-memory
-// wavefronts and the instructions per pair — the two resources the fp32 form saturates (ncu: LSU 86 %,
-// issue 74 %).  Because the bounds are conservative, pruning stays exact:
+// The reference abandons a row once its partial distance over the leading (highest-variance) subspaces
+// reaches the running k-th best (VAQ.cpp:1708); on its data ~95 % of the (row, query) pairs die after the
+// first group of four.  The shared-memory tables here hold, for a tile of eight queries,
+//     e16[s][c][t] = round_toward_zero_fp16( scale_t * lut[t][s][c] ),     t = 0..7
+// (written by lut_build_kernel<8> together with the fp32 tables; scale_t is a per-query power of two), i.e.
+// guaranteed LOWER bounds of the reference's table entries, 16 bytes per code: one LDS.128 returns the
+// entries of all eight queries, and four HADD2 accumulate them.
 //
-//   stage 1   acc = e16_0 + e16_1 + e16_2 + e16_3 in packed half2 arithmetic (round-to-nearest: at most
-//             (1+2^-11)^3 above the real sum), pruned iff acc > RU_fp16(thr * scale * (1 + 2^-9)).  Then the real
-//             partial sum exceeds thr by > 2^-11 relative, far more than the 40 * 2^-24 by which the fp32
-//             distance the reference computes can fall below the real sum  =>  the reference's own distance
-//             is > thr and the row cannot be among the k best.
-//   level 1/2 per-lane lower bound over groups 1-2, then over all subspaces, accumulated in fp32 from the
-//             same fp16 entries, pruned iff LB > thr * scale * (1 + 2^-9).
-//   level 3   the few pairs whose full lower bound is still under the bound are scored EXACTLY from the
-//             fp32 tables in global memory (L2), in the reference's order and grouping
-//             (dism = ((l0+l1)+l2)+l3 ; dist += dism, VAQ.cpp:1741-1748), and only these exact distances
-//             enter the top-k lists and tighten the bounds.
+//   stage 1 (every row)    each lane takes a row, reads only its first 128-bit word (coalesced, prefetched),
+//                          extracts the first group's codes once and accumulates the group for the eight
+//                          queries in packed half2.  Rows with at least one query still under its bound are
+//                          compacted (ballot + popc) into the warp's queue as (row, query mask).
+//   level 1 / level 2      32 queued rows per pass, one per lane: the row's words are fetched once into
+//                          registers, the lower bound over groups 1-2 (level 1) / all subspaces (level 2) is
+//                          accumulated for all eight queries the same way, and the query mask shrinks.
+//   level 3 (exact)        rows that still have a query under its bound are scored EXACTLY for those queries
+//                          from the fp32 tables in global memory (L2), in the reference's order and grouping
+//                          (dism = ((l0+l1)+l2)+l3 ; dist += dism, VAQ.cpp:1741-1748).  Only these exact
+//                          distances enter the top-k lists and tighten the bounds.
 //
-// Result: bit-identical to the fp32 kernels (tests/test_gpu_vaq.py runs all three against the oracle).
+// Exactness of the pruning.  Entries are rounded toward zero, half2 additions round to nearest: after n
+// additions the accumulated value is at most (1+2^-11)^n above the real sum of the (scaled) entries.  A pair
+// is dropped only if its accumulated value exceeds  RU_fp16(thr * scale * (1+m))  with m = 2^-9 after the
+// 3 additions of stage 1, 2^-7 after 7 (level 1), 2^-5 after <= 127 ... capped at 31 additions for M <= 32 and
+// m = 2^-3 beyond (level 2).  Then the real partial sum exceeds thr by more than 2^-11 relative, far more than
+// the ~M * 2^-24 by which the fp32 distance the reference computes can fall below the real sum, so the
+// reference's own distance is > thr and the row cannot be among the k best.  Result: bit-identical to the fp32
+// kernels (tests/test_gpu_vaq.py runs all three against the oracle).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -33,9 +39,7 @@ namespace vaqgpu {
 namespace {
 
 constexpr int T8 = 8;
-constexpr int kQ1Cap16 = 32 + 32 * T8;   // 31 pending + one tile's pushes for 8 queries
-constexpr int kQCap = 64;                // level-2 / level-3 queues: 31 pending + one drain
-constexpr float kMargin = 1.0f + 1.0f / 512.0f;
+constexpr int kQCap = 64;                // every queue: at most 31 pending + 32 pushed by one pass
 
 __device__ __forceinline__ uint32_t half_bits_ru(float x) { return (uint32_t)__half_as_ushort(__float2half_ru(x)); }
 
@@ -55,6 +59,16 @@ __device__ __forceinline__ uint32_t bytes_to_nibble(uint32_t b) { return ((b & 0
 
 __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
 
+// 8-bit mask of the queries whose accumulated lower bound is above the bound stored at `s_thr` (8 x u32, fp16 bits)
+__device__ __forceinline__ uint32_t dead_mask(const __half2 (&acc)[4], uint32_t s_thr) {
+  const uint4 th0 = lds128_volatile(s_thr), th1 = lds128_volatile(s_thr + 16);
+  const uint32_t m0 = __hgt2_mask(acc[0], as_h2(__byte_perm(th0.x, th0.y, 0x5410)));
+  const uint32_t m1 = __hgt2_mask(acc[1], as_h2(__byte_perm(th0.z, th0.w, 0x5410)));
+  const uint32_t m2 = __hgt2_mask(acc[2], as_h2(__byte_perm(th1.x, th1.y, 0x5410)));
+  const uint32_t m3 = __hgt2_mask(acc[3], as_h2(__byte_perm(th1.z, th1.w, 0x5410)));
+  return bytes_to_nibble(__byte_perm(m0, m1, 0x6420)) | (bytes_to_nibble(__byte_perm(m2, m3, 0x6420)) << 4);
+}
+
 }  // namespace
 
 // FAST1: the first group has four fields that all start in the row's first 32-bit word (e.g. four 9- or
@@ -68,28 +82,39 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   const int q0 = qt * T8;
 
   const size_t lut_bytes = (size_t)a.lut_stride * T8 * sizeof(__half);       // multiple of 64
-  const __half *slut = reinterpret_cast<const __half *>(smem_raw);
   uint32_t *thr_f = reinterpret_cast<uint32_t *>(smem_raw + lut_bytes);      // [8] exact k-th distance bits (fp32)
-  uint32_t *thr_h = thr_f + 8;                                               // [8] fp16 bits of RU(thr * scale * margin)
-  float *scale_m = reinterpret_cast<float *>(thr_h + 8);                     // [8] scale * margin
-  uint32_t *locks = reinterpret_cast<uint32_t *>(scale_m + 8);               // [8]
+  uint32_t *thr_h = thr_f + 8;                                               // [3][8] fp16 bits of RU(thr * scale * margin_l)
+  float *scale_s = reinterpret_cast<float *>(thr_h + 24);                    // [8] scale
+  uint32_t *locks = reinterpret_cast<uint32_t *>(scale_s + 8);               // [8]
   uint64_t *lists = reinterpret_cast<uint64_t *>(locks + 8);                 // [8][k] ascending exact keys
   uint64_t *bar = lists + (size_t)T8 * k;
-  uint32_t *queues = reinterpret_cast<uint32_t *>(bar + 1);                  // per warp: q1 | q2e | q2d | q3
+  uint32_t *queues = reinterpret_cast<uint32_t *>(bar + 1);                  // per warp: q1 | q2 | q3, (row << 8) | query mask
 
   const unsigned char *g16 = reinterpret_cast<const unsigned char *>(a.lut16) + (size_t)qt * lut_bytes;
   const float *g32 = a.lut32 + (size_t)qt * a.lut_stride * T8;
+  const int M = a.lay.M;
+  const float margin[3] = {1.f + 1.f / 512.f, 1.f + 1.f / 128.f, M <= 32 ? 1.f + 1.f / 32.f : 1.f + 1.f / 8.f};
+
+  // (called by one thread per query) publish a new exact bound: the three fp16 bounds follow the fp32 one
+  auto publish_bound = [&](int t, uint32_t bits) {
+    atomicMin(thr_f + t, bits);
+    const float v = __uint_as_float(bits) * scale_s[t];
+#pragma unroll
+    for (int l = 0; l < 3; l++) atomicMin(thr_h + l * 8 + t, half_bits_ru(v * margin[l]));
+  };
 
   for (int i = tid; i < T8 * k; i += blockDim.x) lists[i] = kEmptyKey;
   if (tid < T8) {
     const int q = min(q0 + tid, a.nq - 1);
-    const float sm = a.scale[q0 + tid] * kMargin;
     const uint32_t g = a.thr_global[q];
-    scale_m[tid] = sm;
+    const float sc = a.scale[q0 + tid];
+    scale_s[tid] = sc;
     thr_f[tid] = g;
     // queries past nq (padding of the last tile) get the bound -1.0: every lower bound is above it, so they
     // never survive stage 1 and nothing ever updates the slot
-    thr_h[tid] = (q0 + tid < a.nq) ? half_bits_ru(__uint_as_float(g) * sm) : 0xBC00u;
+#pragma unroll
+    for (int l = 0; l < 3; l++)
+      thr_h[l * 8 + tid] = (q0 + tid < a.nq) ? half_bits_ru(__uint_as_float(g) * sc * margin[l]) : 0xBC00u;
     locks[tid] = 0u;
   }
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -104,26 +129,26 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   mbar_wait(bar, 0);
 
   // stage-1 program: the first group (<= 4 fields, <= 60 bits, i.e. inside 32-bit words 0..2)
-  const int M = a.lay.M;
   const int G1 = min(4, M);
-  uint32_t s1_sh[4], s1_mask[4], s1_off[4];
+  uint32_t s1_sh[4], s1_mask[4], s1_addr[4];
   bool s1_hi[4];
+  const uint32_t s_base = smem_u32(smem_raw);
+  const uint32_t s_thr_h = smem_u32(thr_h);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const int f = min(i, G1 - 1);
     const uint32_t meta = a.lay.fmeta[f];
     s1_sh[i] = meta & 31u;
     s1_mask[i] = meta >> 16;
-    s1_off[i] = a.lay.foff[f] * (T8 * 2);          // byte offset of the table
+    s1_addr[i] = s_base + a.lay.foff[f] * (T8 * 2);          // shared address of the table
     s1_hi[i] = a.lay.fword[f] != 0;
   }
   const bool two_level = M > 8;
   const int F2 = two_level ? 8 : M;
 
-  uint32_t *q1 = queues + (size_t)warp * (kQ1Cap16 + 3 * kQCap);
-  uint32_t *q2e = q1 + kQ1Cap16;
-  float *q2d = reinterpret_cast<float *>(q2e + kQCap);
-  uint32_t *q3 = q2e + 2 * kQCap;
+  uint32_t *q1 = queues + (size_t)warp * (3 * kQCap);
+  uint32_t *q2 = q1 + kQCap;
+  uint32_t *q3 = q2 + kQCap;
   int q1n = 0, q2n = 0, q3n = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -140,11 +165,66 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   if (tl + nwarps < tile_end) nxt = ldg_stream_u4(pnext);
   int refresh = 0;
   const uint32_t rows_here = (uint32_t)(min(a.n_rows, tile_end << 5) - row_base);    // valid rows of this chunk
-  const uint32_t s_base = smem_u32(smem_raw);
-  const uint32_t s_thr_h = smem_u32(thr_h);
-  uint32_t s1_addr[4];
+
+  // ---- bound seeding ---------------------------------------------------------------------------------
+  // A CTA that starts without bounds has to score everything it sees exactly.  Each lane scores a few sample
+  // rows of the chunk for all eight queries from the fp16 tables; since e16 >= scale * entry * (1 - 2^-11)
+  // (round toward zero) and the half2 sums are at most (1+2^-11)^M off, acc * (1 + 1/16) / scale is an UPPER
+  // bound of the row's distance.  The k-th smallest of the per-warp minima of these upper bounds belongs to k
+  // distinct rows, hence bounds the k-th best distance.
+  if (a.seed && k <= nwarps && rows_here >= (uint32_t)blockDim.x * 4u * 8u && M <= 64) {
+    const uint32_t step = rows_here / (blockDim.x * 4u);
+    __half2 best[4];
+    best[0] = best[1] = best[2] = best[3] = as_h2(0x7C007C00u);        // +inf
+    for (int j = 0; j < 4; j++) {
+      const int64_t row = row_base + (int64_t)((uint32_t)(j * (int)blockDim.x + tid) * step);
+      const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
+      __half2 acc[4];
+      acc[0] = acc[1] = acc[2] = acc[3] = as_h2(0u);
+      for (int f = 0; f < M; f++) {
+        const uint32_t meta = a.lay.fmeta[f];
+        const uint32_t lo = __ldg(rp + a.lay.fw_lo[f]), hi = __ldg(rp + a.lay.fw_hi[f]);
+        const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
+        const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
+        acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
+        acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+      }
 #pragma unroll
-  for (int i = 0; i < 4; i++) s1_addr[i] = s_base + s1_off[i];
+      for (int i = 0; i < 4; i++) best[i] = __hmin2(best[i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t *>(&best[i]), o);
+        best[i] = __hmin2(best[i], as_h2(other));
+      }
+    }
+    __syncthreads();
+    float *allmin = reinterpret_cast<float *>(queues);      // [nwarps][8]; the queues are still empty
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float2 v = __half22float2(best[i]);
+        allmin[warp * T8 + 2 * i] = v.x;
+        allmin[warp * T8 + 2 * i + 1] = v.y;
+      }
+    }
+    __syncthreads();
+    if (tid < T8 && q0 + tid < a.nq) {
+      const float *col = allmin + tid;
+      float kth = __uint_as_float(0x7f800000u);
+      for (int i = 0; i < nwarps; i++) {
+        const float x = col[i * T8];
+        int rank = 0;
+        for (int j = 0; j < nwarps; j++) rank += (col[j * T8] < x) || (col[j * T8] == x && j < i);
+        if (rank == k - 1) kth = x;
+      }
+      const float ub = kth * (1.f + 1.f / 16.f) / scale_s[tid] * (1.f + 1e-6f) + 1e-30f;
+      if (ub < 3.0e38f) publish_bound(tid, __float_as_uint(ub));
+    }
+    __syncthreads();
+  }
 
   while (true) {
     const bool more = tl < tile_end;
@@ -161,30 +241,16 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
       }
     }
     if (level) {
-      // ---- survivors: one code site for the two lower-bound levels and the exact level ----------------
+      // ---- 32 queued rows, one per lane (single code site for the three levels) -----------------------
       __syncwarp();
       const bool active = lane < take;
       uint32_t e = 0u;
-      float dist = 0.f;
-      int fb = 0, fe = M;
-      if (level == 1) {
-        if (active) e = q1[q1n - take + lane];
-        q1n -= take;
-        fe = F2;
-      } else if (level == 2) {
-        if (active) { e = q2e[q2n - take + lane]; dist = q2d[q2n - take + lane]; }
-        q2n -= take;
-        fb = F2;
-      } else {
-        if (active) e = q3[q3n - take + lane];
-        q3n -= take;
-      }
-      const bool exact = level == 3;
-      const int t = (int)(e & 7u);
-      const int64_t row = row_base + (e >> 3);
+      if (level == 1) { if (active) e = q1[q1n - take + lane]; q1n -= take; }
+      else if (level == 2) { if (active) e = q2[q2n - take + lane]; q2n -= take; }
+      else { if (active) e = q3[q3n - take + lane]; q3n -= take; }
+      unsigned mask = e & 0xFFu;                      // queries of the tile still alive for this row (0 when inactive)
+      const int64_t row = row_base + (e >> 8);
       const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
-      float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
-      if (!exact) thr *= scale_m[t];
       // Rows of up to 256 bits are fetched once (W 16-byte loads per lane) and walked from registers: the
       // fields come in increasing bit order, so a two-word window (lo, hi) slides over the eight words and a
       // word is picked by a select tree on the (warp-uniform) word index.  A 4-byte load per field would
@@ -208,52 +274,64 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
       };
       int widx = -2;
       uint32_t lo = 0u, hi = 0u;
-      bool alive = true;
-      for (int g = fb; g < fe; g += 4) {
-        float dism = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int f = g + j;
-          if (f < fe) {
-            const uint32_t meta = a.lay.fmeta[f];
-            if constexpr (W <= 2) {
-              const int fw = a.lay.fword[f];
-              if (fw != widx) {
-                lo = (fw == widx + 1) ? hi : selw(fw);
-                hi = selw(fw + 1);
-                widx = fw;
-              }
-            } else {
-              lo = __ldg(rp + a.lay.fw_lo[f]);
-              hi = __ldg(rp + a.lay.fw_hi[f]);
-            }
-            const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
-            const uint32_t idx = (a.lay.foff[f] + code) * T8 + t;
-            dism += exact ? __ldg(g32 + idx) : __half2float(slut[idx]);
+      auto field_code = [&](int f) -> uint32_t {      // code of field f of this lane's row
+        const uint32_t meta = a.lay.fmeta[f];
+        if constexpr (W <= 2) {
+          const int fw = a.lay.fword[f];
+          if (fw != widx) {
+            lo = (fw == widx + 1) ? hi : selw(fw);
+            hi = selw(fw + 1);
+            widx = fw;
           }
-        }
-        dist += dism;
-        if (__all_sync(0xffffffffu, !active || (dist > thr))) { alive = false; break; }
-      }
-      if (alive) {
-        if (!exact) {
-          // still under the bound: next level
-          const bool s = active && !(dist > thr);
-          const unsigned m = __ballot_sync(0xffffffffu, s);
-          const bool to_q2 = level == 1 && two_level;
-          if (s) {
-            if (to_q2) {
-              const int pos = q2n + __popc(m & lt_mask);
-              q2e[pos] = e;
-              q2d[pos] = dist;
-            } else {
-              q3[q3n + __popc(m & lt_mask)] = e;
-            }
-          }
-          if (to_q2) q2n += __popc(m); else q3n += __popc(m);
         } else {
-          const uint64_t key = active ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
-          const uint64_t kth0 = active ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
+          lo = __ldg(rp + a.lay.fw_lo[f]);
+          hi = __ldg(rp + a.lay.fw_hi[f]);
+        }
+        return __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
+      };
+
+      if (level < 3) {
+        // lower bounds of all eight queries over fields [0, fe), packed half2
+        const int fe = level == 1 ? F2 : M;
+        __half2 acc[4];
+        acc[0] = acc[1] = acc[2] = acc[3] = as_h2(0u);
+        for (int f = 0; f < fe; f++) {
+          const uint32_t code = field_code(f);
+          const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
+          acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
+          acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+        }
+        mask &= ~dead_mask(acc, s_thr_h + level * 32);
+        const unsigned m = __ballot_sync(0xffffffffu, mask != 0);
+        const bool to_q2 = level == 1 && two_level;
+        if (mask) {
+          const uint32_t ne = (e & ~0xFFu) | mask;
+          if (to_q2) q2[q2n + __popc(m & lt_mask)] = ne; else q3[q3n + __popc(m & lt_mask)] = ne;
+        }
+        if (to_q2) q2n += __popc(m); else q3n += __popc(m);
+      } else {
+        // exact distances, one (row, query) pair per lane and pass, until every lane's mask is empty
+        while (__any_sync(0xffffffffu, mask != 0)) {
+          const bool act = mask != 0;
+          const int t = act ? (__ffs(mask) - 1) : 0;
+          mask &= mask - 1;
+          const float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
+          widx = -2;
+          float dist = 0.f;
+          bool alive = true;
+          for (int g = 0; g < M; g += 4) {
+            float dism = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int f = g + j;
+              if (f < M) dism += __ldg(g32 + (a.lay.foff[f] + field_code(f)) * T8 + t);
+            }
+            dist += dism;
+            if (__all_sync(0xffffffffu, !act || (dist > thr))) { alive = false; break; }
+          }
+          if (!alive) continue;
+          const uint64_t key = act ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
+          const uint64_t kth0 = act ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
           unsigned m = __ballot_sync(0xffffffffu, key < kth0);
           while (m) {
             const int src = __ffs(m) - 1;
@@ -266,8 +344,17 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
               c = __shfl_sync(0xffffffffu, c, 0);      // one observer: the decision must be warp-uniform
               if (!(kk < c)) continue;
             }
-            if (lane == 0) while (atomicCAS(locks + tt, 0u, 1u) != 0u) __nanosleep(200);
-            __syncwarp();
+            // take the query's list lock; give up as soon as the list has moved past this candidate
+            int got = 0;
+            if (lane == 0) {
+              while (true) {
+                if (!(kk < lst[k - 1])) break;
+                if (atomicCAS(locks + tt, 0u, 1u) == 0u) { got = 1; break; }
+                __nanosleep(100);
+              }
+            }
+            got = __shfl_sync(0xffffffffu, got, 0);
+            if (!got) continue;
             const uint64_t before = lst[k - 1];
             const uint64_t kth = warp_list_insert(lst, k, kk, lane);
             __syncwarp();
@@ -276,9 +363,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
               atomicExch(locks + tt, 0u);
               if (kth != before && kth != kEmptyKey) {
                 const uint32_t bits = (uint32_t)(kth >> 32);
-                atomicMin(thr_f + tt, bits);
-                atomicMin(thr_h + tt, half_bits_ru(__uint_as_float(bits) * scale_m[tt]));
-                if (q0 + tt < a.nq) atomicMin(a.thr_global + q0 + tt, bits);
+                publish_bound(tt, bits);
+                atomicMin(a.thr_global + q0 + tt, bits);
               }
             }
           }
@@ -295,12 +381,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     if (((++refresh) & 31) == 0 && lane < T8 && q0 + lane < a.nq) {
       // pick up bounds published by other row chunks of this query tile
       const uint32_t g = *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane);
-      if (g < *reinterpret_cast<volatile uint32_t *>(thr_f + lane)) {
-        atomicMin(thr_f + lane, g);
-        atomicMin(thr_h + lane, half_bits_ru(__uint_as_float(g) * scale_m[lane]));
-      }
+      if (g < *reinterpret_cast<volatile uint32_t *>(thr_f + lane)) publish_bound(lane, g);
     }
-    const uint4 th0 = lds128_volatile(s_thr_h), th1 = lds128_volatile(s_thr_h + 16);
     __half2 acc[4];
 #pragma unroll
     for (int i1 = 0; i1 < 4; i1++) {
@@ -315,31 +397,14 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
         }
       }
     }
-    // per query: is the partial lower bound above the bound?  (0xFFFF per half that is)
-    const uint32_t m0 = __hgt2_mask(acc[0], as_h2(__byte_perm(th0.x, th0.y, 0x5410)));
-    const uint32_t m1 = __hgt2_mask(acc[1], as_h2(__byte_perm(th0.z, th0.w, 0x5410)));
-    const uint32_t m2 = __hgt2_mask(acc[2], as_h2(__byte_perm(th1.x, th1.y, 0x5410)));
-    const uint32_t m3 = __hgt2_mask(acc[3], as_h2(__byte_perm(th1.z, th1.w, 0x5410)));
-    const uint32_t dead = bytes_to_nibble(__byte_perm(m0, m1, 0x6420)) | (bytes_to_nibble(__byte_perm(m2, m3, 0x6420)) << 4);
     const uint32_t rel = ((uint32_t)(tl - tile_begin) << 5) + lane;
-    unsigned sb = ~dead & 0xFFu;
+    unsigned sb = ~dead_mask(acc, s_thr_h) & 0xFFu;
     if (tl == tile_end - 1 && rel >= rows_here) sb = 0u;      // only the last tile of the index can be partial
-    if (__any_sync(0xffffffffu, sb != 0)) {
-      // compact the surviving (row, query) pairs into the warp's queue: exclusive scan of the per-lane counts
-      const int cnt = __popc(sb);
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      int pos = q1n + incl - cnt;
-      while (sb) {
-        const int t = __ffs(sb) - 1;
-        sb &= sb - 1;
-        q1[pos++] = (rel << 3) | (uint32_t)t;
-      }
-      q1n += __shfl_sync(0xffffffffu, incl, 31);
+    {
+      // compact the rows that still have a live query into the warp's queue
+      const unsigned m = __ballot_sync(0xffffffffu, sb != 0);
+      if (sb) q1[q1n + __popc(m & lt_mask)] = (rel << 8) | sb;
+      q1n += __popc(m);
     }
     tl += nwarps;
   }
@@ -355,9 +420,9 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
 
 size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads) {
   const int nwarps = threads / 32;
-  size_t b = (size_t)lut_stride * T8 * 2 + 4 * 32;
+  size_t b = (size_t)lut_stride * T8 * 2 + 6 * 32;          // tables + bounds/scales/locks
   b += ((size_t)T8 * k + 1) * sizeof(uint64_t);
-  b += (size_t)nwarps * (kQ1Cap16 + 3 * kQCap) * sizeof(uint32_t);
+  b += (size_t)nwarps * (3 * kQCap) * sizeof(uint32_t);
   return b;
 }
 

@@ -205,6 +205,7 @@ struct AdcFilter16Args {
   int32_t chunk_tiles, out_slots, slot_base;
   uint64_t *out_keys;
   uint32_t *thr_global;
+  int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
   ScanLayout lay;
 };
 size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads);

@@ -356,6 +356,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles;
       a.out_keys = (uint64_t *)h->w_keys.p;
       a.thr_global = (uint32_t *)h->w_thr.p;
+      a.seed = tune_knob("seed", 1);
       a.lay = lay;
       CU(launch_adc_filter16_scan(a, threads, smem, st));
       launches++;
