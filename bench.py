@@ -306,13 +306,23 @@ def run_gpu_arm(args, w, name):
     scan_ms_mean = float(np.mean(scan_ms))
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes_step / (scan_ms_mean / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "adc_filter_scan_kernel" if cfg["scan_kernel"] == 2 else "adc_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
+    kname = {1: "adc_scan_kernel", 2: "adc_filter_scan_kernel", 3: "adc_filter16_scan_kernel"}.get(cfg["scan_kernel"], "adc_scan_kernel")
+    traffic = None
+    try:        # DRAM bytes per launch of this kernel on this workload from the committed ncu --set full capture
+        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        ent = tj.get(kname, {})
+        if ent.get("workload") == name and ent.get("n_gpus") == world:
+            traffic = ent.get("dram_bytes_read", 0) + ent.get("dram_bytes_write", 0)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
                 "launch_ms": scan_ms_mean / n_launch, "query_tile_T": T,
                 "pairs_per_s": nq * n_local / (scan_ms_mean / 1e3),
                 "note": ("SURVEY 8d accounting: ceil(nq/T) passes over the packed rows (T queries share each pass) + LUT/result bytes; "
                          f"at this shape the packed codes ({n_local * row_bytes / 1e6:.0f} MB) are L2-resident and the scan is bound by "
-                         "shared-memory LUT gathers, not HBM — see roofline_hbm_shape for the same kernel on a shard >> L2")}
+                         "shared-memory LUT gathers (ncu: LSU pipe 87 %, issue 62 %, DRAM 1.5 %), not HBM; `traffic` = ncu DRAM bytes "
+                         "of one launch — see roofline_hbm_shape for the same kernel on a shard >> L2")}
 
     # ---- the same kernel on a shard far larger than L2 (the HBM-bound regime of the 100M / 1B-row shapes)
     hbm_shape = None
