@@ -73,31 +73,30 @@ __global__ void __launch_bounds__(256) lut_build_kernel(const float *__restrict_
   const int qt = blockIdx.y;
   const int L = p.L;
   if (lut16 != nullptr) {
-    if (threadIdx.x < 32) {
-      for (int t = 0; t < T; t++) {
-        const int q = min(qt * T + t, nq - 1);
-        float ub = 0.f;
-        for (int s = threadIdx.x; s < p.M; s += 32) {
-          const float *qs = q_proj + (size_t)q * D + (size_t)s * L;
-          float n2 = 0.f;
-          for (int j = 0; j < L; j++) n2 = fmaf(qs[j], qs[j], n2);
-          const float r = sqrtf(n2) + cent_rmax[s];
-          ub = fmaxf(ub, r * r);
-        }
+    const int t = threadIdx.x >> 5, ln = threadIdx.x & 31;       // one warp per query of the tile
+    if (t < T) {
+      const int q = min(qt * T + t, nq - 1);
+      float ub = 0.f;
+      for (int s = ln; s < p.M; s += 32) {
+        const float *qs = q_proj + (size_t)q * D + (size_t)s * L;
+        float n2 = 0.f;
+        for (int j = 0; j < L; j++) n2 = fmaf(qs[j], qs[j], n2);
+        const float r = sqrtf(n2) + cent_rmax[s];
+        ub = fmaxf(ub, r * r);
+      }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ub = fmaxf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
-        if (threadIdx.x == 0) {
-          float sc = 1.f;
-          ub *= 1.0001f;                       // the entries are computed with rounding; keep a hair of slack
-          if (ub > 0.f && ub < 3.0e38f) {
-            int ex = (int)floorf(log2f(16000.f / ub));
-            ex = max(-100, min(100, ex));
-            sc = exp2f((float)ex);
-            while (ub * sc > 16000.f) sc *= 0.5f;
-          }
-          sscale[t] = sc;
-          if (blockIdx.x == 0) scale[qt * T + t] = sc;
+      for (int o = 16; o > 0; o >>= 1) ub = fmaxf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+      if (ln == 0) {
+        float sc = 1.f;
+        ub *= 1.0001f;                       // the entries are computed with rounding; keep a hair of slack
+        if (ub > 0.f && ub < 3.0e38f) {
+          int ex = (int)floorf(log2f(16000.f / ub));
+          ex = max(-100, min(100, ex));
+          sc = exp2f((float)ex);
+          while (ub * sc > 16000.f) sc *= 0.5f;
         }
+        sscale[t] = sc;
+        if (blockIdx.x == 0) scale[qt * T + t] = sc;
       }
     }
     __syncthreads();
