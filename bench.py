@@ -32,6 +32,8 @@ WORKLOADS = {
     # name: rows, dims, budget, M, min_bits, max_bits, queries, k, decay
     "sift1m_256b_m32_k10": dict(n=1_000_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0),
     "small_256b_m32_k10": dict(n=100_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=1_000, k=10, decay=4.0),
+    "shard125k_256b_m32_k10": dict(n=125_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0),
+    "tiny16k_256b_m32_k10": dict(n=16_384, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0),
 }
 TRAIN_ROWS = 32768
 SEED = 13517106

@@ -172,18 +172,48 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   // (round toward zero) and the half2 sums are at most (1+2^-11)^M off, acc * (1 + 1/16) / scale is an UPPER
   // bound of the row's distance.  The k-th smallest of the per-warp minima of these upper bounds belongs to k
   // distinct rows, hence bounds the k-th best distance.
-  if (a.seed && k <= nwarps && rows_here >= (uint32_t)blockDim.x * 4u * 8u && M <= 64) {
-    const uint32_t step = rows_here / (blockDim.x * 4u);
+  const int spl = (int)min(4u, rows_here / (blockDim.x * 4u));      // sample rows per lane: at most a quarter of the chunk
+  if (a.seed && k <= nwarps && spl >= 1 && M <= 64) {
+    const uint32_t step = rows_here / (blockDim.x * (uint32_t)spl);
     __half2 best[4];
     best[0] = best[1] = best[2] = best[3] = as_h2(0x7C007C00u);        // +inf
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < spl; j++) {
       const int64_t row = row_base + (int64_t)((uint32_t)(j * (int)blockDim.x + tid) * step);
       const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
+      uint32_t wd[8];
+      if constexpr (W <= 2) {           // row words once into registers (same sliding window as the queue passes)
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(rp));
+        wd[0] = v0.x; wd[1] = v0.y; wd[2] = v0.z; wd[3] = v0.w;
+        if constexpr (W == 2) {
+          const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(rp) + kTileRows);
+          wd[4] = v1.x; wd[5] = v1.y; wd[6] = v1.z; wd[7] = v1.w;
+        } else {
+          wd[4] = wd[5] = wd[6] = wd[7] = 0u;
+        }
+      }
+      auto selw = [&](int i) -> uint32_t {
+        const uint32_t s0 = (i & 1) ? wd[1] : wd[0], s1 = (i & 1) ? wd[3] : wd[2];
+        const uint32_t s2 = (i & 1) ? wd[5] : wd[4], s3 = (i & 1) ? wd[7] : wd[6];
+        const uint32_t t0 = (i & 2) ? s1 : s0, t1 = (i & 2) ? s3 : s2;
+        return (i & 8) ? 0u : ((i & 4) ? t1 : t0);
+      };
+      int widx = -2;
+      uint32_t lo = 0u, hi = 0u;
       __half2 acc[4];
       acc[0] = acc[1] = acc[2] = acc[3] = as_h2(0u);
       for (int f = 0; f < M; f++) {
         const uint32_t meta = a.lay.fmeta[f];
-        const uint32_t lo = __ldg(rp + a.lay.fw_lo[f]), hi = __ldg(rp + a.lay.fw_hi[f]);
+        if constexpr (W <= 2) {
+          const int fw = a.lay.fword[f];
+          if (fw != widx) {
+            lo = (fw == widx + 1) ? hi : selw(fw);
+            hi = selw(fw + 1);
+            widx = fw;
+          }
+        } else {
+          lo = __ldg(rp + a.lay.fw_lo[f]);
+          hi = __ldg(rp + a.lay.fw_hi[f]);
+        }
         const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
         const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
         acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
@@ -211,17 +241,19 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
       }
     }
     __syncthreads();
-    if (tid < T8 && q0 + tid < a.nq) {
-      const float *col = allmin + tid;
-      float kth = __uint_as_float(0x7f800000u);
-      for (int i = 0; i < nwarps; i++) {
-        const float x = col[i * T8];
-        int rank = 0;
-        for (int j = 0; j < nwarps; j++) rank += (col[j * T8] < x) || (col[j * T8] == x && j < i);
-        if (rank == k - 1) kth = x;
+    if (warp < T8 && q0 + warp < a.nq) {
+      // warp t ranks the nwarps minima of query t: lane i owns minimum i, the lane of rank k-1 publishes
+      const float *col = allmin + warp;
+      const float x = lane < nwarps ? col[lane * T8] : __uint_as_float(0x7f800000u);
+      int rank = 0;
+      for (int j = 0; j < nwarps; j++) {
+        const float y = col[j * T8];
+        rank += (y < x) || (y == x && j < lane);
       }
-      const float ub = kth * (1.f + 1.f / 16.f) / scale_s[tid] * (1.f + 1e-6f) + 1e-30f;
-      if (ub < 3.0e38f) publish_bound(tid, __float_as_uint(ub));
+      if (lane < nwarps && rank == k - 1) {
+        const float ub = x * (1.f + 1.f / 16.f) / scale_s[warp] * (1.f + 1e-6f) + 1e-30f;
+        if (ub < 3.0e38f) publish_bound(warp, __float_as_uint(ub));
+      }
     }
     __syncthreads();
   }
