@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     for (int l = 0; l < 3; l++) atomicMin(thr_h + l * 8 + t, half_bits_ru(v * margin[l]));
   };
 
+  long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && tid == 0) dbg[0] = clock64();
   for (int i = tid; i < T8 * k; i += blockDim.x) lists[i] = kEmptyKey;
   if (tid < T8) {
     const int q = min(q0 + tid, a.nq - 1);
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     }
   }
   mbar_wait(bar, 0);
+  if (dbg && tid == 0) dbg[1] = clock64();
 
   // stage-1 program: the first group (<= 4 fields, <= 60 bits, i.e. inside 32-bit words 0..2)
   const int G1 = min(4, M);
@@ -257,9 +260,12 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     }
     __syncthreads();
   }
+  if (dbg && tid == 0) dbg[2] = clock64();
+  int dbg_tail = 0;
 
   while (true) {
     const bool more = tl < tile_end;
+    if (dbg && !more && !dbg_tail && tid == 0) { dbg[3] = clock64(); dbg_tail = 1; }
     int level = 0, take = 0;
     if (((q1n | q2n | q3n) >= 32) || !more) {           // rarely true: keep the common path to one test
       if (q3n >= 32) { level = 3; take = 32; }
@@ -442,7 +448,9 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   }
 
   // ---- CTA epilogue: publish this (query tile, chunk)'s keys -----------------------------------------
+  if (dbg && tid == 0) dbg[4] = clock64();
   __syncthreads();
+  if (dbg && tid == 0) dbg[5] = clock64();
   for (int i = tid; i < T8 * k; i += blockDim.x) {
     const int t = i / k, j = i - t * k;
     const int q = q0 + t;

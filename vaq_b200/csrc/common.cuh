@@ -206,6 +206,7 @@ struct AdcFilter16Args {
   uint64_t *out_keys;
   uint32_t *thr_global;
   int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
+  long long *dbg;            // development: per-CTA phase clocks (NULL = off)
   ScanLayout lay;
 };
 size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads);

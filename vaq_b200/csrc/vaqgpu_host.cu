@@ -114,7 +114,7 @@ struct vaqgpu_index {
   bool timed = false;
   int32_t cfg[12] = {};
 
-  DevBuf w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
+  DevBuf w_dbg, w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
 };
 
 struct hamgpu_index {
@@ -360,7 +360,20 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.thr_global = (uint32_t *)h->w_thr.p;
       a.seed = tune_knob("seed", 1);
       a.lay = lay;
+      const bool dbg = tune_knob("dbg", 0) != 0;
+      const size_t n_cta = (size_t)((qb + T - 1) / T) * n_chunks;
+      if (dbg) { CU(h->w_dbg.ensure(n_cta * 8 * sizeof(long long))); a.dbg = (long long *)h->w_dbg.p; }
       CU(launch_adc_filter16_scan(a, threads, smem, st));
+      if (dbg) {        // development only: per-CTA phase durations in SM clocks
+        std::vector<long long> hd(n_cta * 8);
+        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpy(hd.data(), h->w_dbg.p, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        double ph[5] = {0, 0, 0, 0, 0};
+        for (size_t c = 0; c < n_cta; c++)
+          for (int i = 0; i < 5; i++) ph[i] += (double)(hd[c * 8 + i + 1] - hd[c * 8 + i]);
+        fprintf(stderr, "[vaqgpu dbg] per-CTA clocks: table staging %.0f, seeding %.0f, scan (warp 0) %.0f, warp-0 tail %.0f, wait for other warps %.0f\n",
+                ph[0] / n_cta, ph[1] / n_cta, ph[2] / n_cta, ph[3] / n_cta, ph[4] / n_cta);
+      }
       launches++;
       if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
       CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)out_slots * k, out_slots, qb, k, want_sqrt ? 1 : 0, 0,
@@ -604,7 +617,7 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   cudaFree(h->d_centroids); cudaFree(h->d_cent_rmax); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
   cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size);
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
-  for (DevBuf *b : {&h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
+  for (DevBuf *b : {&h->w_dbg, &h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
                     &h->w_labels, &h->w_dists, &h->w_outkeys, &h->w_cdf, &h->w_x})
     b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
