@@ -216,11 +216,26 @@ def run_gpu_arm(args, w, name):
     flags = EA | PROJECTED | (0x1000 if args.scan_v1 else 0)
 
     # index: this rank's row block, encoded on the device (bit-exact vs the oracle, tests/test_gpu_vaq.py)
-    sh = ShardedVAQ(model.L, model.bits, model.centroids, model.eig, n, rank, world, local_rank)
+    # Layout.  --row-shards R: R ranks share one copy of the code matrix (row-sharded), world/R replica groups split
+    # the query batch.  Default ("auto"): the fewest row shards that keep a GPU's share of the packed matrix under
+    # 16 GiB — a 32 MB matrix is replicated, a 1B-row one is row-sharded.  The pure row-sharded layout BASELINE.json
+    # names (R = N) is always timed as well (`row_sharded_layout` in the JSON line).
+    packed_bytes = n * 16 * (-(-w["budget"] // 128))
+    R = args.row_shards
+    if not R:
+        R = 1
+        while R < world and packed_bytes / R > (16 << 30):
+            R *= 2
+    sh = ShardedVAQ(model.L, model.bits, model.centroids, model.eig, n, rank, world, local_rank, row_shards=R)
     t0 = time.time()
     sh.index.encode_add(XP[sh.lo:sh.hi])
     log(f"[bench] rank {rank}: encoded rows [{sh.lo},{sh.hi}) in {time.time() - t0:.1f}s; row_bytes={sh.index.row_bytes}")
     ix = sh.index
+
+    sh_rows = None
+    if world > 1 and sh.R < world:
+        sh_rows = ShardedVAQ(model.L, model.bits, model.centroids, model.eig, n, rank, world, local_rank, row_shards=world)
+        sh_rows.index.encode_add(XP[sh_rows.lo:sh_rows.hi])
 
     d_q = torch.from_numpy(Q).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -263,6 +278,28 @@ def run_gpu_arm(args, w, name):
     total_ms = float(total_ms.item())
     value = nq * args.steps / (total_ms / 1e3)
 
+    # ---- the same steps on the pure row-sharded layout (N shards, all queries on every rank), when it is not the default
+    row_layout = None
+    if sh_rows is not None:
+        for _ in range(args.warmup):
+            sh_rows.search(d_q, k, flags)
+        barrier()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            barrier()
+            ev2[i][0].record(st)
+            rl, rd = sh_rows.search(d_q, k, flags)
+            ev2[i][1].record(st)
+            torch.cuda.synchronize()
+        barrier()
+        t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(rl, labels) and torch.equal(rd.view(torch.int32), dists.view(torch.int32)))
+        row_layout = {"sharding": f"rows/{world}", "value": nq * args.steps / (float(t2.item()) / 1e3), "unit": "queries/s",
+                      "ms_per_step": float(t2.item()) / args.steps, "identical_to_default_layout": same,
+                      "scan_ms": sh_rows.index.last_timings()["scan_ms"]}
+
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region
     q_pin = torch.from_numpy(Q).pin_memory()
     lab_pin = torch.empty((nq, k), dtype=torch.int32).pin_memory()
@@ -299,12 +336,14 @@ def run_gpu_arm(args, w, name):
     # ---- roofline of the dominant kernel (ADC scan), T = 1 accounting (each query's CTAs stream the rows)
     cfg = ix.last_config()
     n_local = sh.hi - sh.lo
+    qa, qb_ = sh.query_slice(nq)
+    nq_rank = qb_ - qa                       # queries this rank's replica group answers
     row_bytes = ix.row_bytes
     lut_bytes = int(ix.lut_size) * 4
-    n_launch = -(-nq // cfg["queries_per_launch"])
+    n_launch = -(-nq_rank // cfg["queries_per_launch"])
     T = max(1, cfg["queries_per_cta"])
     # one pass over the local rows per query TILE (T queries share the stream) + per-query LUT and result bytes
-    alg_bytes_step = -(-nq // T) * n_local * row_bytes + nq * (lut_bytes + k * 8 * cfg["row_chunks"])
+    alg_bytes_step = -(-nq_rank // T) * n_local * row_bytes + nq_rank * (lut_bytes + k * 8 * cfg["row_chunks"])
     scan_ms_mean = float(np.mean(scan_ms))
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes_step / (scan_ms_mean / 1e3) / 1e9
@@ -320,7 +359,7 @@ def run_gpu_arm(args, w, name):
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
                 "launch_ms": scan_ms_mean / n_launch, "query_tile_T": T,
-                "pairs_per_s": nq * n_local / (scan_ms_mean / 1e3),
+                "pairs_per_s": nq_rank * n_local / (scan_ms_mean / 1e3),
                 "note": ("SURVEY 8d accounting: ceil(nq/T) passes over the packed rows (T queries share each pass) + LUT/result bytes; "
                          f"at this shape the packed codes ({n_local * row_bytes / 1e6:.0f} MB) are L2-resident and the scan is bound by "
                          "shared-memory LUT gathers (ncu: LSU pipe 87 %, issue 62 %, DRAM 1.5 %), not HBM; `traffic` = ncu DRAM bytes "
@@ -389,7 +428,22 @@ def run_gpu_arm(args, w, name):
     # ---- CPU baseline on the box's host cores + parity of the returned neighbours on the same queries
     cpu = None
     parity = None
-    if not args.no_cpu:
+    if not args.no_cpu and world > 1:
+        # multi-GPU: the merged answer of the first queries against the oracle's canonical answer on the whole matrix
+        from oracle import oracle as orc
+        om = orc.Model(model.L, model.bits, model.centroids)
+        nchk = 32
+        try:        # torchrun exports OMP_NUM_THREADS=1; the checker may use the idle host cores
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(max(1, (os.cpu_count() or 1) // 2))
+        except OSError:
+            pass
+        codes_all = orc.Port().encode(om, XP)
+        wl, wd = orc.Port().search_lex(om, codes_all, Q[:nchk], k)
+        glab, gdis = lab_pin.numpy()[:nchk], dis_pin.numpy()[:nchk]
+        parity = {"queries": nchk, "checker": "oracle port, whole matrix", "ids_equal_frac": float((glab == wl).mean()),
+                  "dists_bit_equal": bool(np.array_equal(gdis.view(np.uint32), wd.view(np.uint32)))}
+    if not args.no_cpu and world == 1:
         codes_local = ix.get_codes()
         if world == 1:
             threads = os.cpu_count() or 1
@@ -410,12 +464,14 @@ def run_gpu_arm(args, w, name):
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "rows": n, "dims": w["d"], "queries": nq, "k": k, "bits": w["budget"], "subspaces": w["M"],
-                   "mode": "EA", "row_bytes": row_bytes, "sharding": f"rows/{world}", "l2": "256 MB fill between timed steps",
+                   "mode": "EA", "row_bytes": row_bytes,
+                   "sharding": f"rows/{sh.R}" + (f" x queries/{sh.qgroups} (matrix replicated {sh.qgroups}x)" if sh.qgroups > 1 else ""), "l2": "256 MB fill between timed steps",
                    "scan_config": cfg},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(Q.nbytes), "d2h_bytes_per_step": int(nq * k * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "row_sharded_layout": row_layout,
         "roofline_hbm_shape": hbm_shape,
         "hamming_scan": hamming,
         "cpu_baseline": cpu,
@@ -441,6 +497,9 @@ def main():
     ap.add_argument("--no-hbm-shape", action="store_true")
     ap.add_argument("--hbm-rows", type=int, default=64_000_000)
     ap.add_argument("--scan-v1", action="store_true", help="force the lane-per-row scan kernel (comparison)")
+    ap.add_argument("--row-shards", type=int, default=0,
+                    help="R: ranks per replica group (default N = pure row sharding, the BASELINE layout); R < N replicates the "
+                         "code matrix N/R times and splits the query batch between the groups")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]

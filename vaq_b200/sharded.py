@@ -52,14 +52,26 @@ def allgather_keys(local_keys, group=None):
 
 
 class ShardedVAQ:
-    """One rank's share of a row-sharded VAQ index.  All ranks hold the same model and receive the
-    same query batch; each scans its own rows."""
+    """One rank's share of a VAQ index spread over the GPUs of one box.
 
-    def __init__(self, L, bits, centroids, eig, n_rows_total: int, rank: int, world: int, device: int, group=None):
+    ``row_shards`` = R (default: world size, i.e. pure row sharding).  The ranks form ``world // R`` replica
+    groups of R ranks: inside a group the code matrix is row-sharded (rank ``r = rank % R`` holds block r of R),
+    and each group answers its own contiguous slice of the query batch.  All ranks hold the same model and
+    receive the same query batch; one all-gather of the shard-local top-k key lists plus a device merge per
+    query slice gives every rank the full answer.  R = world is the layout BASELINE.json names; R < world trades
+    HBM (the matrix is replicated world/R times) for throughput when the index is small."""
+
+    def __init__(self, L, bits, centroids, eig, n_rows_total: int, rank: int, world: int, device: int, group=None,
+                 row_shards: int | None = None):
         from .index import VAQIndex
-        self.rank, self.world, self.group = rank, world, group
-        self.bounds = shard_bounds(n_rows_total, world)
-        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        R = world if not row_shards else int(row_shards)
+        if R < 1 or world % R:
+            raise ValueError(f"row_shards={R} must divide the world size {world}")
+        self.rank, self.world, self.group, self.R = rank, world, group, R
+        self.qgroups = world // R
+        self.r, self.qg = rank % R, rank // R
+        self.bounds = shard_bounds(n_rows_total, R)
+        self.lo, self.hi = self.bounds[self.r], self.bounds[self.r + 1]
         self.index = VAQIndex(L, bits, centroids, eig=eig, device=device)
         self.index.set_id_base(self.lo)
         self.index.reserve(max(1, self.hi - self.lo))
@@ -71,19 +83,29 @@ class ShardedVAQ:
     def add_synthetic(self, seed: int, cdf=None):
         self.index.add_synthetic(self.hi - self.lo, seed, cdf)
 
+    def query_slice(self, nq: int) -> tuple[int, int]:
+        """Queries [a, b) this rank's replica group answers (equal slices, padded at the end)."""
+        per = -(-nq // self.qgroups)
+        return min(self.qg * per, nq), min((self.qg + 1) * per, nq)
+
     def search(self, d_queries, k: int, flags: int):
         """d_queries: CUDA float32 tensor [nq, D], identical on every rank.  Returns (labels int32 [nq,k],
         dists float32 [nq,k]) CUDA tensors, identical on every rank."""
         import torch
         nq = d_queries.shape[0]
         st = torch.cuda.current_stream().cuda_stream
-        keys = torch.empty((nq, k), dtype=torch.int64, device=d_queries.device)
-        self.index.search_keys_device(d_queries.data_ptr(), nq, k, flags, keys.data_ptr(), st)
-        allk = allgather_keys(keys, self.group)
-        labels = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
-        dists = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
-        self.index.merge_keys_device(allk.data_ptr(), self.world, nq, k, flags, labels.data_ptr(), dists.data_ptr(), st)
-        return labels, dists
+        per = -(-nq // self.qgroups)
+        a, b = self.query_slice(nq)
+        keys = torch.full((per, k), -1, dtype=torch.int64, device=d_queries.device)      # -1 == empty key
+        if b > a:
+            self.index.search_keys_device(d_queries[a:b].data_ptr(), b - a, k, flags, keys.data_ptr(), st)
+        allk = allgather_keys(keys, self.group)                     # [world][per][k], rank = qg * R + r
+        labels = torch.empty((self.qgroups * per, k), dtype=torch.int32, device=d_queries.device)
+        dists = torch.empty((self.qgroups * per, k), dtype=torch.float32, device=d_queries.device)
+        for g in range(self.qgroups):
+            self.index.merge_keys_device(allk[g * self.R].data_ptr(), self.R, per, k, flags, labels[g * per].data_ptr(),
+                                         dists[g * per].data_ptr(), st)
+        return labels[:nq], dists[:nq]
 
 
 class ShardedHamming:
