@@ -1,38 +1,34 @@
-// ADC scan, filter-and-refine form — the kernel behind VAQ::searchEarlyAbandon (reference
-// bitvecengine/VAQ.cpp:1694-1727) for whole-index scans.
+// ADC scan, filter-and-refine on fp32 tables — the fallback kernel behind VAQ::searchEarlyAbandon (reference
+// bitvecengine/VAQ.cpp:1694-1727) for the cases the fp16 form (adc_filter16_scan.cu) does not take: tables too
+// large for eight queries in shared memory (T = 1..4, with the trailing tables spilled to L2 when even one
+// query's tables do not fit — GIST-512-bit / 13-15-bit subspaces), very large k, or fewer than five queries.
 //
-// The reference abandons a row as soon as its partial distance over the leading subspaces
-// reaches the running k-th best (VAQ.cpp:1708); the subspaces are in variance-descending order,
-// so on the reference's data > 95 % of the rows die after the first group of four.  A lane-per-row
-// GPU loop cannot exploit that (a warp only stops when all 32 rows are dead), so the scan is split:
+// The reference abandons a row as soon as its partial distance over the leading subspaces reaches the
+// running k-th best (VAQ.cpp:1708); the subspaces are in variance-descending order, so on the reference's
+// data > 95 % of the rows die after the first group of four.  A lane-per-row GPU loop cannot exploit that (a
+// warp only stops when all 32 rows are dead), so the scan is split:
 //
-//  stage 1 (every row):   one CTA owns a tile of T queries and a chunk of rows.  The T lookup
-//      tables sit in shared memory interleaved per entry ([entry][T]), so ONE 16/32-byte shared load
-//      returns the table values of all T queries for a row's code.  Each lane takes a row, reads only
-//      the first 128-bit word of it (coalesced, prefetched three tiles ahead), extracts the first
-//      group's codes once and accumulates the first group for all T queries in the reference's
-//      order, dism = ((l0+l1)+l2)+l3.  (row, query) pairs whose partial distance already exceeds the
-//      query's running k-th best are dropped — exactly the reference's first abandon test.
-//  stage 2 (survivors):   surviving pairs are compacted into a per-warp queue; whenever 32 are
-//      pending the warp scores them with full lanes — reloads the row's words, walks ALL subspaces
-//      in the reference's order and grouping (so the distance is bit-identical to searchHeap's),
-//      abandoning when every lane is dead, and inserts the finishers into the per-(warp, query)
-//      sorted top-k lists.
+//  stage 1 (every row):   one CTA owns a tile of T queries and a chunk of rows.  The T lookup tables sit in
+//      shared memory interleaved per entry ([entry][T]), so ONE shared load returns the table values of all T
+//      queries for a row's code.  Each lane takes a row, reads only the first 128-bit word of it (coalesced,
+//      two tiles prefetched in registers), extracts the first group's codes once and accumulates the first
+//      group for all T queries in the reference's order, dism = ((l0+l1)+l2)+l3.  (row, query) pairs whose
+//      partial distance already exceeds the query's running k-th best are dropped — exactly the reference's
+//      first abandon test.
+//  stage 2 (survivors):   surviving pairs are compacted into per-warp queues (ballot + popc); whenever 32 are
+//      pending the warp scores them with full lanes in two levels (groups 1-2, then the rest), the row's words
+//      fetched once into registers, walking the subspaces in the reference's order and grouping (so the
+//      distance is bit-identical to searchHeap's), abandoning when every lane is dead, and inserts the
+//      finishers into the CTA's per-query sorted top-k list under a per-query lock.
 //
-// Thresholds only ever come from k rows that were really scored, so the pruning is exact: the
-// result is the k lexicographically smallest (distance, row) keys, independent of scheduling.
-// A per-query threshold in global memory lets later row chunks (and later launches) start from
-// the bound earlier chunks reached.
+// Bounds only ever come from k rows that were really scored, so the pruning is exact: the result is the k
+// lexicographically smallest (distance, row) keys, independent of scheduling.  A per-query bound in global
+// memory lets later row chunks start from the bound earlier chunks reached; each CTA also seeds its bounds
+// from the per-warp minima of a few sample rows.
 #include "common.cuh"
 
 namespace vaqgpu {
 
-
-template <int T> struct LutVec;
-template <> struct LutVec<1> { float v[1]; };
-template <> struct LutVec<2> { float v[2]; };
-template <> struct LutVec<4> { float v[4]; };
-template <> struct LutVec<8> { float v[8]; };
 
 template <int T>
 __device__ __forceinline__ void lds_vec(float (&out)[T], const float *p) {
@@ -294,7 +290,6 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
   // scores a few sample rows of the chunk exactly for all T queries and keeps the minimum per query:
   // the k-th smallest of the nwarps minima is the distance of k distinct rows, hence a valid bound.
   if (a.seed && k <= nwarps && (tile_end - tile_begin) * kTileRows >= (int64_t)blockDim.x * kSeedRowsPerLane * 8) {
-    float *wmin = reinterpret_cast<float *>(q1);      // the warp's queue space is still free
     const int64_t rows_here = min(a.n_rows, tile_end << 5) - row_base;
     const int64_t step = rows_here / ((int64_t)blockDim.x * kSeedRowsPerLane);
     float best[T];
@@ -333,7 +328,6 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
       atomicMin(thr_f + tid, __float_as_uint(kth));
     }
     __syncthreads();
-    (void)wmin;
   }
 
   int64_t tl = tile_begin + warp;
