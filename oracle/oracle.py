@@ -230,6 +230,39 @@ class Ref:
     def nproc(self) -> int:
         return int(self.lib.ref_nproc())
 
+    # -- on-disk formats as written / read by the reference's own utils/IO.hpp
+    def save_codebook(self, path: str, codes) -> None:
+        codes = np.ascontiguousarray(codes, np.uint16)
+        self.lib.ref_save_codebook(str(path).encode(), _ptr(codes, C.c_uint16), C.c_long(codes.shape[0]), codes.shape[1])
+
+    def load_codebook(self, path: str, cap: int = 1 << 24) -> np.ndarray:
+        buf = np.empty(cap, np.uint16)
+        M = C.c_int(0)
+        self.lib.ref_load_codebook.restype = C.c_long
+        n = self.lib.ref_load_codebook(str(path).encode(), _ptr(buf, C.c_uint16), C.c_long(cap), C.byref(M))
+        return buf[: n * M.value].reshape(n, M.value).copy()
+
+    def save_centroids(self, path: str, m: "Model") -> None:
+        self.lib.ref_save_centroids(str(path).encode(), m.M, m.L, _ptr(m.bits, C.c_int), _ptr(m.cent_flat, C.c_float))
+
+    def load_centroids_flat(self, path: str, cap: int = 1 << 24):
+        buf = np.empty(cap, np.float32)
+        M, L = C.c_int(0), C.c_int(0)
+        self.lib.ref_load_centroids.restype = C.c_long
+        n = self.lib.ref_load_centroids(str(path).encode(), _ptr(buf, C.c_float), C.c_long(cap), C.byref(M), C.byref(L))
+        return buf[:n].copy(), M.value, L.value
+
+    def read_fvecs(self, path: str, dim: int, rows: int) -> np.ndarray:
+        out = np.zeros((rows, dim), np.float32)
+        self.lib.ref_read_fvecs(str(path).encode(), dim, _ptr(out, C.c_float), C.c_long(rows))
+        return out
+
+    def read_ivecs(self, path: str, dim: int, cap_rows: int) -> np.ndarray:
+        out = np.zeros((cap_rows, dim), np.int32)
+        self.lib.ref_read_ivecs.restype = C.c_long
+        n = self.lib.ref_read_ivecs(str(path).encode(), dim, _ptr(out, C.c_int), C.c_long(cap_rows))
+        return out[:n]
+
 
 class RefVAQ:
     def __init__(self, ref: Ref, m: Model, methods: int, eig_real):

@@ -37,6 +37,7 @@
 #include "VAQ.hpp"
 #undef private
 #include "BitVecEngine.hpp"
+#include "utils/IO.hpp"
 
 namespace {
 /* The reference prints progress to std::cout (e.g. VAQ.cpp:910,976); silence it. */
@@ -261,6 +262,54 @@ void ref_generate_dummy(int nbits, int size, int seed, uint64_t *out) {
 void ref_create_bitv(int nbits, uint64_t raw, uint64_t *out) {
   bitv v = createBitV(nbits, raw);
   std::memcpy(out, v.data(), sizeof(uint64_t) * v.size());
+}
+
+/* ---- on-disk formats (utils/IO.hpp) — lets the tests check vaq_b200/io.py against files the reference
+ * itself writes and reads: saveCentroids/loadCentroids (:736, :522), saveCodebook/loadCodebook (:757, :552),
+ * readFVecsFromExternal (:126), readIVecsFromExternal (:334) */
+void ref_save_codebook(const char *path, const uint16_t *codes, long n, int M) {
+  CodebookType cb = Eigen::Map<const CodebookType>(codes, n, M);
+  saveCodebook<CodebookType>(cb, path);
+}
+long ref_load_codebook(const char *path, uint16_t *out, long cap, int *M) {
+  CodebookType cb = loadCodebook<CodebookType>(path);
+  *M = (int)cb.cols();
+  if ((long)cb.size() <= cap) std::memcpy(out, cb.data(), sizeof(uint16_t) * cb.size());
+  return cb.rows();
+}
+void ref_save_centroids(const char *path, int M, int L, const int *bits, const float *centroids) {
+  CentroidsPerSubsType c((size_t)M);
+  size_t off = 0;
+  for (int s = 0; s < M; s++) {
+    const long K = 1L << bits[s];
+    c[(size_t)s] = Eigen::Map<const CentroidsMatType>(centroids + off, K, L);
+    off += (size_t)K * L;
+  }
+  saveCentroids(c, path);
+}
+long ref_load_centroids(const char *path, float *out, long cap, int *M, int *L) {
+  CentroidsPerSubsType c = loadCentroids(path);
+  *M = (int)c.size();
+  *L = c.empty() ? 0 : (int)c[0].cols();
+  long n = 0;
+  for (const CentroidsMatType &m : c) {
+    if (n + (long)m.size() <= cap) std::memcpy(out + n, m.data(), sizeof(float) * m.size());
+    n += (long)m.size();
+  }
+  return n;
+}
+long ref_read_fvecs(const char *path, int dim, float *out, long max_rows) {
+  RowMatrixXf d = RowMatrixXf::Zero(max_rows, dim);
+  CoutSilencer quiet;
+  readFVecsFromExternal(path, d, dim, (int)max_rows);
+  std::memcpy(out, d.data(), sizeof(float) * (size_t)max_rows * dim);
+  return max_rows;
+}
+long ref_read_ivecs(const char *path, int dim, int *out, long cap_rows) {
+  std::vector<std::vector<int>> d;
+  readIVecsFromExternal(path, d, dim);
+  for (size_t i = 0; i < d.size() && (long)i < cap_rows; i++) std::memcpy(out + i * dim, d[i].data(), sizeof(int) * dim);
+  return (long)d.size();
 }
 
 int ref_nproc(void) { return omp_get_num_procs(); }
