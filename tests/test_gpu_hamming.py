@@ -102,3 +102,37 @@ def test_synthetic_rows_and_shard_merge():
         assert np.array_equal(dist.cpu().numpy().view(np.uint32), ld), f"G={G}"
         for ix in shards:
             ix.close()
+
+
+def test_large_synthetic_bitvectors_planted_needles():
+    """10M on-device synthetic 256-bit rows (C5-style generator): every query is a row of the index with a few
+    bits flipped -> that row must come back first with exactly that distance; returned distances equal the
+    popcounts of the (host-regenerated) returned rows; a host-regenerated 1M-row slice holds no unreturned row
+    under the k-th distance."""
+    from vaq_b200 import synth
+    n, nq, k, seed, nbits = 10_000_000, 40, 10, 99, 256
+    rng = np.random.default_rng(5)
+    planted = rng.integers(0, n, size=nq)
+    q = np.concatenate([synth.synth_bitvectors(1, int(r), nbits, seed) for r in planted])
+    flips = rng.integers(0, 6, size=nq)
+    for i in range(nq):
+        for b in rng.choice(nbits, size=int(flips[i]), replace=False):
+            q[i, b // 64] ^= np.uint64(1) << np.uint64(b % 64)
+    ix = make(nbits)
+    ix.add_synthetic(n, seed)
+    idx, dist = ix.query(q, k)
+    assert np.array_equal(idx[:, 0], planted) and np.array_equal(dist[:, 0], flips.astype(np.uint32))
+    assert (np.diff(dist.astype(np.int64), axis=1) >= 0).all()
+    for i in range(0, nq, 8):
+        rows = np.concatenate([synth.synth_bitvectors(1, int(r), nbits, seed) for r in idx[i]])
+        x = rows ^ q[i][None, :]
+        pc = np.unpackbits(x.view(np.uint8).reshape(k, -1), axis=1).sum(1)
+        assert np.array_equal(pc, dist[i])
+    lo = 6_000_000
+    sl = synth.synth_bitvectors(1_000_000, lo, nbits, seed)
+    for i in range(0, nq, 8):
+        x = sl ^ q[i][None, :]
+        d = np.unpackbits(x.view(np.uint8).reshape(sl.shape[0], -1), axis=1).sum(1, dtype=np.int64)
+        better = np.nonzero(d < int(dist[i, -1]))[0] + lo
+        assert set(better.tolist()) <= set(idx[i].tolist())
+    ix.close()
