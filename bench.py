@@ -43,6 +43,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly one JSON line: everything else any library prints at the C level (e.g. NCCL's version
+# banner) is sent to stderr by pointing fd 1 at fd 2 for the whole run and keeping the real stdout aside.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def build_problem(w: dict):
     """Seeded synthetic base/queries + host-trained model (the reference keeps training on the host)."""
     from vaq_b200 import synth, train
@@ -184,7 +206,7 @@ def run_reference_arm(args, w, name):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -479,7 +501,7 @@ def run_gpu_arm(args, w, name):
         "kernel_ms": {"lut_build": float(np.mean(lut_ms)), "adc_scan": scan_ms_mean, "merge": float(np.mean(merge_ms))},
         "step_ms_rank0": [float(x) for x in step_ms],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -501,6 +523,7 @@ def main():
                     help="R: ranks per replica group (default N = pure row sharding, the BASELINE layout); R < N replicates the "
                          "code matrix N/R times and splits the query batch between the groups")
     args = ap.parse_args()
+    capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
