@@ -438,3 +438,21 @@ def test_large_synthetic_index_planted_needles_and_slices(port):
         lab2, dis2 = ix.search(Q, k, EA | PROJECTED | extra)
         assert np.array_equal(lab2, lab) and bitwise_equal(dis2, dis)
     ix.close()
+
+
+@pytest.mark.parametrize("M,bits_of", [(48, lambda s: 6 if s < 24 else 5),      # 264 bits -> 3 words per row (generic word path), M > 32 margins
+                                       (40, lambda s: 6),                         # 240 bits, M > 32
+                                       (64, lambda s: 5 if s < 32 else 4),        # 288 bits, M = 64
+                                       (12, lambda s: 10 if s < 4 else 7)])       # four 10-bit leading fields (FAST1 boundary: 0,10,20,30)
+def test_search_many_subspaces_fp16_path(port, M, bits_of):
+    from vaq_b200.index import EA, PROJECTED
+    rng = np.random.default_rng(M)
+    bits = [bits_of(s) for s in range(M)]
+    m = random_model(rng, M, 2, bits)
+    codes = random_codes(rng, m, 60000)
+    Q = rng.standard_normal((19, m.D)).astype(np.float32)
+    ix = make_index(m, codes=codes)
+    check_search(port, m, codes, Q, 10, EA, ix=ix)
+    ix.search(Q, 10, EA | PROJECTED)
+    assert ix.last_config()["scan_kernel"] == 3
+    ix.close()
