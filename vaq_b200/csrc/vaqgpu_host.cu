@@ -423,8 +423,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     if (n_chunks > 65535) return fail(VAQGPU_EINVAL, "index too large for one launch (%lld chunks)", (long long)n_chunks);
 
-    const int n_warm = 0;
-    const int out_slots = (int)n_chunks + n_warm;
+    const int out_slots = (int)n_chunks;
 
     CU(h->w_lut.ensure((size_t)qb_max * bytes_per_q));
     CU(h->w_keys.ensure((size_t)qb_max * out_slots * k * sizeof(uint64_t)));
@@ -447,7 +446,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.thr_global = (uint32_t *)h->w_thr.p;
       a.lay = lay;
       a.seed = tune_knob("seed", 1);
-      a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles; a.slot_base = n_warm;
+      a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles; a.slot_base = 0;
       CU(launch_adc_filter_scan(a, T, threads, smem, st));
       launches++;
       if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
