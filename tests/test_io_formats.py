@@ -68,6 +68,14 @@ def test_files_interchange_with_the_reference(tmp_path):
     assert np.array_equal(ref.read_ivecs(tmp_path / "g.ivecs", 100, 10), iv)
 
 
+def test_query_fixture_is_the_shipped_file():
+    from helpers import GOLDEN
+    q = vio.read_fvecs(GOLDEN / "siftsmall_query.fvecs")
+    assert q.shape == (100, 128) and q.min() >= 0 and q.max() <= 255
+    if (REF_DATA / "siftsmall_query.fvecs").exists():
+        assert (GOLDEN / "siftsmall_query.fvecs").read_bytes() == (REF_DATA / "siftsmall_query.fvecs").read_bytes()
+
+
 @pytest.mark.skipif(not (REF_DATA / "siftsmall_query.fvecs").exists(), reason="reference data not mounted")
 def test_shipped_siftsmall_files():
     q = vio.read_fvecs(REF_DATA / "siftsmall_query.fvecs")
