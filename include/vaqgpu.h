@@ -86,7 +86,7 @@ int vaqgpu_encode_add(vaqgpu_t *h, const float *x_proj, int64_t n);
 /* Append n rows generated on the device: code[i][s] = inverse-CDF(hash(seed, id_base+i, s)).
  * `cdf` is the concatenation over s of 2^bits[s] cumulative probabilities (last = 1), or NULL
  * for uniform codes.  Used for the 100M / 1B-row shapes the host cannot hold; the same
- * generator is restated in numpy (vaq_b200/synth_codes.py) for CPU parity on row slices. */
+ * generator is restated in numpy (vaq_b200/synth.py) for CPU parity on row slices. */
 int vaqgpu_add_codes_synthetic(vaqgpu_t *h, int64_t n, uint64_t seed, const float *cdf);
 
 /* Pre-size the packed code matrix for n_total rows (avoids regrowth copies on 100M+ row shards). */

@@ -3,7 +3,7 @@
 Two checkers live behind this module:
 
 * ``Port``  — oracle/libvaq_oracle.so, the plain-C restatement (oracle/vaq_oracle.c).
-  Travels to the GPU box; pinned against the reference by tests/test_oracle_vs_ref.py
+  Travels to the GPU box; pinned against the reference by tests/test_oracle_golden.py
   and the committed tests/golden fixtures.
 * ``Ref``   — oracle/_ref/libvaq_ref.so, the UNMODIFIED reference compiled from
   /root/reference by oracle/Makefile (present whenever build() ran in a container
@@ -251,6 +251,17 @@ class Ref:
         self.lib.ref_load_centroids.restype = C.c_long
         n = self.lib.ref_load_centroids(str(path).encode(), _ptr(buf, C.c_float), C.c_long(cap), C.byref(M), C.byref(L))
         return buf[:n].copy(), M.value, L.value
+
+    def read_bitv_csv(self, path: str, cols: int, cap_rows: int) -> np.ndarray:
+        w = (cols + 63) // 64
+        out = np.zeros((cap_rows, w), np.uint64)
+        self.lib.ref_read_bitv_csv.restype = C.c_long
+        n = self.lib.ref_read_bitv_csv(str(path).encode(), cols, _ptr(out, C.c_uint64), C.c_long(cap_rows))
+        return out[:n]
+
+    def write_bitv_csv(self, path: str, words, nbits: int) -> None:
+        words = np.ascontiguousarray(words, np.uint64)
+        self.lib.ref_write_bitv_csv(str(path).encode(), _ptr(words, C.c_uint64), C.c_long(words.shape[0]), nbits)
 
     def read_fvecs(self, path: str, dim: int, rows: int) -> np.ndarray:
         out = np.zeros((rows, dim), np.float32)

@@ -312,6 +312,22 @@ long ref_read_ivecs(const char *path, int dim, int *out, long cap_rows) {
   return (long)d.size();
 }
 
+/* bit-vector CSV: readFromExternal(filepath, bitvectors&, cols, delim) (utils/IO.hpp:363-397) and
+ * writeToExternal(filepath, const bitvectors&, N) (:681-704) */
+long ref_read_bitv_csv(const char *path, int cols, uint64_t *out, long cap_rows) {
+  bitvectors bv;
+  readFromExternal(std::string(path), bv, cols, ',');
+  const int w = actualBitVLen(cols);
+  for (size_t i = 0; i < bv.size() && (long)i < cap_rows; i++) std::memcpy(out + i * w, bv[i].data(), sizeof(uint64_t) * w);
+  return (long)bv.size();
+}
+void ref_write_bitv_csv(const char *path, const uint64_t *words, long n, int nbits) {
+  const int w = actualBitVLen(nbits);
+  bitvectors bv((size_t)n, bitv((size_t)w, 0));
+  for (long i = 0; i < n; i++) std::memcpy(bv[(size_t)i].data(), words + (size_t)i * w, sizeof(uint64_t) * w);
+  writeToExternal(std::string(path), bv, nbits);
+}
+
 int ref_nproc(void) { return omp_get_num_procs(); }
 
 }  /* extern "C" */

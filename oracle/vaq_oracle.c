@@ -3,7 +3,7 @@
  * it is never shipped, never imported by vaq_b200/, and never the thing measured
  * (except as bench.py's cpu_baseline "port" leg when oracle/_ref is absent).
  *
- * Parity status: PINNED.  tests/test_oracle_vs_ref.py checks every function here
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function here
  * against oracle/_ref/libvaq_ref.so (the unmodified reference compiled from
  * /root/reference, see oracle/Makefile) on seeded inputs, and against the
  * reference's own known-answer tests (test/test-distancefunction.cpp:11-63,

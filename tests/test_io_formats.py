@@ -87,3 +87,51 @@ def test_shipped_siftsmall_files():
         ref = orc.Ref()
         assert np.array_equal(ref.read_fvecs(REF_DATA / "siftsmall_query.fvecs", 128, 100), q)
         assert np.array_equal(ref.read_ivecs(REF_DATA / "siftsmall_groundtruth.ivecs", 100, 200), gt)
+
+
+# ---- bit-vector CSV + createBitV (utils/IO.hpp:363-397, 681-704; BitVector.hpp:46-76) -------------------------
+
+def test_create_bitv_known_answers():
+    # the reference's own uses (test/test-distancefunction.cpp, test-bitvecengine.cpp): N <= 64 scalar, lists beyond
+    assert vio.create_bitv(1, 1).tolist() == [1]
+    assert vio.create_bitv(32, 0xDEADBEEF).tolist() == [0xDEADBEEF]
+    assert vio.create_bitv(64, 0xFFFFFFFFFFFFFFFF).tolist() == [0xFFFFFFFFFFFFFFFF]
+    assert vio.create_bitv(256, [1, 2, 3, 4]).tolist() == [1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        vio.create_bitv(256, [1, 2, 3])
+    assert vio.actual_bitv_len(1) == 1 and vio.actual_bitv_len(64) == 1 and vio.actual_bitv_len(65) == 2
+
+
+def test_bitvector_csv_round_trip(tmp_path):
+    rng = np.random.default_rng(3)
+    for nbits in (64, 128, 256):
+        bv = rng.integers(0, 2 ** 63, size=(17, nbits // 64), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(17, nbits // 64), dtype=np.uint64)
+        vio.write_bitvectors_csv(tmp_path / f"b{nbits}.csv", bv, nbits)
+        first = (tmp_path / f"b{nbits}.csv").read_text().splitlines()[0].split(",")
+        assert len(first) == nbits and first[0] == str(int(bv[0, 0]) >> 63)      # MSB first
+        assert np.array_equal(vio.read_bitvectors_csv(tmp_path / f"b{nbits}.csv", nbits), bv)
+
+
+@pytest.mark.skipif(not orc.Ref.available(), reason="compiled reference not built")
+@pytest.mark.parametrize("nbits", [1, 31, 64, 65, 100, 128, 200, 256])
+def test_bitvector_csv_interchange_with_the_reference(tmp_path, nbits):
+    """Files written by either side are byte-identical, and both readers return the same words — including the
+    reference reader's behaviour on a partial last word (see vaq_b200/io.py::read_bitvectors_csv)."""
+    ref = orc.Ref()
+    rng = np.random.default_rng(nbits)
+    w = (nbits + 63) // 64
+    bv = rng.integers(0, 2 ** 63, size=(9, w), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(9, w), dtype=np.uint64)
+    rem = nbits - (w - 1) * 64
+    if rem < 64:        # writeToExternal prints the TOP `rem` bits of the last word
+        bv[:, -1] &= ~np.uint64((1 << (64 - rem)) - 1)
+    ref.write_bitv_csv(tmp_path / "ref.csv", bv, nbits)
+    vio.write_bitvectors_csv(tmp_path / "mine.csv", bv, nbits)
+    assert (tmp_path / "ref.csv").read_bytes() == (tmp_path / "mine.csv").read_bytes()
+    got_ref = ref.read_bitv_csv(tmp_path / "mine.csv", nbits, 64)
+    got_mine = vio.read_bitvectors_csv(tmp_path / "ref.csv", nbits)
+    assert np.array_equal(got_ref, got_mine)
+    if nbits % 64 == 0:
+        assert np.array_equal(got_mine, bv)
+    for raw in (0, 1, 0x8000000000000001, 0x123456789ABCDEF0):
+        for n in (1, 17, 64):
+            assert np.array_equal(ref.create_bitv(n, raw), vio.create_bitv(n, raw))

@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   uint32_t *q2 = q1 + kQCap;
   uint32_t *q3 = q2 + kQCap;
   int q1n = 0, q2n = 0, q3n = 0;
+  // Bounds only tighten when the exact level runs.  Waiting for 32 pending rows per warp is right in steady state
+  // (full lanes) but on a short chunk most of it would be scanned under the seed bound: the first exact passes of
+  // a warp run as soon as 4, 8, 16 rows are pending (bias 28 -> 24 -> 16 -> 0).
+  int q3_bias = 28;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   const int64_t tile_begin = a.tile_lo + (int64_t)chunk * a.chunk_tiles;
@@ -171,12 +175,15 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
 
   // ---- bound seeding ---------------------------------------------------------------------------------
   // A CTA that starts without bounds has to score everything it sees exactly.  Each lane scores a few sample
-  // rows of the chunk for all eight queries from the fp16 tables; since e16 >= scale * entry * (1 - 2^-11)
-  // (round toward zero) and the half2 sums are at most (1+2^-11)^M off, acc * (1 + 1/16) / scale is an UPPER
-  // bound of the row's distance.  The k-th smallest of the per-warp minima of these upper bounds belongs to k
-  // distinct rows, hence bounds the k-th best distance.
+  // rows of the chunk for all eight queries from the fp16 tables and keeps its minimum per query.  Error budget:
+  // e16 = RZ_fp16(scale * entry) loses < 2^-10 relative on normal values and < 2^-24 absolute on subnormal ones
+  // (scaled entries below 2^-14), the half2 sums lose at most (1+2^-11)^M relative, so
+  //     (acc * (1 + 1/16) + M * 2^-24) / scale
+  // is an UPPER bound of the row's distance (M <= 64: 1.001 * 1.032 < 1.0625).  The lanes' sample rows are
+  // distinct, so the k-th smallest of the per-lane minima is the upper bound of k distinct rows' distances, hence
+  // bounds the k-th best distance of the chunk.
   const int spl = (int)min(4u, rows_here / (blockDim.x * 4u));      // sample rows per lane: at most a quarter of the chunk
-  if (a.seed && k <= nwarps && spl >= 1 && M <= 64) {
+  if (a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64) {
     const uint32_t step = rows_here / (blockDim.x * (uint32_t)spl);
     __half2 best[4];
     best[0] = best[1] = best[2] = best[3] = as_h2(0x7C007C00u);        // +inf
@@ -225,36 +232,36 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
 #pragma unroll
       for (int i = 0; i < 4; i++) best[i] = __hmin2(best[i], acc[i]);
     }
+    // per-lane minima -> shared memory as fp16 bit patterns [8][blockDim] (the queues are still empty); non-negative
+    // halves order like their bit patterns
+    uint16_t *lm = reinterpret_cast<uint16_t *>(queues);
+    const int n = (int)blockDim.x;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t other = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t *>(&best[i]), o);
-        best[i] = __hmin2(best[i], as_h2(other));
-      }
-    }
-    __syncthreads();
-    float *allmin = reinterpret_cast<float *>(queues);      // [nwarps][8]; the queues are still empty
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const float2 v = __half22float2(best[i]);
-        allmin[warp * T8 + 2 * i] = v.x;
-        allmin[warp * T8 + 2 * i + 1] = v.y;
-      }
+      const uint32_t b = *reinterpret_cast<uint32_t *>(&best[i]);
+      lm[(2 * i) * n + tid] = (uint16_t)(b & 0xFFFFu);
+      lm[(2 * i + 1) * n + tid] = (uint16_t)(b >> 16);
     }
     __syncthreads();
     if (warp < T8 && q0 + warp < a.nq) {
-      // warp t ranks the nwarps minima of query t: lane i owns minimum i, the lane of rank k-1 publishes
-      const float *col = allmin + warp;
-      const float x = lane < nwarps ? col[lane * T8] : __uint_as_float(0x7f800000u);
-      int rank = 0;
-      for (int j = 0; j < nwarps; j++) {
-        const float y = col[j * T8];
-        rank += (y < x) || (y == x && j < lane);
+      // warp t: k-th smallest of query t's n minima by bisection over the 15-bit pattern space
+      const uint32_t *col = reinterpret_cast<const uint32_t *>(lm + warp * n);
+      uint32_t lo = 0u, hi = 0x7C00u;                // +inf: fewer than k finite values -> no seed
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        int cnt = 0;
+        for (int i = lane; i < n / 2; i += 32) {
+          const uint32_t v = col[i];
+          cnt += ((v & 0xFFFFu) <= mid) + ((v >> 16) <= mid);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (cnt >= k) hi = mid; else lo = mid + 1;
       }
-      if (lane < nwarps && rank == k - 1) {
-        const float ub = x * (1.f + 1.f / 16.f) / scale_s[warp] * (1.f + 1e-6f) + 1e-30f;
+      if (lane == 0 && lo < 0x7C00u) {
+        const float x = __half2float(__ushort_as_half((unsigned short)lo));
+        const float ub = (x * (1.f + 1.f / 16.f) + (float)M * 5.9604645e-8f) / scale_s[warp] * (1.f + 1e-6f) + 1e-30f;
         if (ub < 3.0e38f) publish_bound(warp, __float_as_uint(ub));
       }
     }
@@ -267,8 +274,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     const bool more = tl < tile_end;
     if (dbg && !more && !dbg_tail && tid == 0) { dbg[3] = clock64(); dbg_tail = 1; }
     int level = 0, take = 0;
-    if (((q1n | q2n | q3n) >= 32) || !more) {           // rarely true: keep the common path to one test
-      if (q3n >= 32) { level = 3; take = 32; }
+    if (((q1n | q2n | (q3n + q3_bias)) >= 32) || !more) {           // rarely true: keep the common path to one test
+      if (q3n + q3_bias >= 32) { level = 3; take = min(q3n, 32); q3_bias = max(0, 2 * q3_bias - 32); }
       else if (q2n >= 32) { level = 2; take = 32; }
       else if (q1n >= 32) { level = 1; take = 32; }
       else if (!more) {
@@ -468,11 +475,10 @@ size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads) {
 
 template <int W, bool FAST1>
 static cudaError_t launch16_wf(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(adc_filter16_scan_kernel<W, FAST1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = optin.ensure(adc_filter16_scan_kernel<W, FAST1>, smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = smem_bytes;
   }
   const int64_t nt = a.tile_hi - a.tile_lo;
   if (nt <= 0) return cudaSuccess;

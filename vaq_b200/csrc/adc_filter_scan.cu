@@ -439,11 +439,10 @@ size_t adc_filter_smem_bytes(int smem_lut_floats, int T, int k, int threads) {
 
 template <int W, int T>
 static cudaError_t launch_wt(const AdcFilterArgs &a, int threads, size_t smem_bytes, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(adc_filter_scan_kernel<W, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = optin.ensure(adc_filter_scan_kernel<W, T>, smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = smem_bytes;
   }
   const int64_t nt = a.tile_hi - a.tile_lo;
   if (nt <= 0) return cudaSuccess;

@@ -157,11 +157,10 @@ __global__ void adc_scan_kernel(const __grid_constant__ AdcScanArgs a) {
 
 template <int W>
 static cudaError_t launch_w(const AdcScanArgs &a, int threads, size_t smem_bytes, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(adc_scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = optin.ensure(adc_scan_kernel<W>, smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = smem_bytes;
   }
   dim3 grid((unsigned)a.splits, (unsigned)a.nq);
   adc_scan_kernel<W><<<grid, threads, smem_bytes, st>>>(a);

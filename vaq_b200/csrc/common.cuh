@@ -49,6 +49,29 @@ __host__ __device__ inline uint64_t make_key_f32(float d, int32_t id) {
 #endif
 }
 
+
+// Opt-in dynamic shared memory (> 48 KB) is a per-DEVICE attribute of a kernel function: a handle on GPU 1 of the
+// same process needs its own cudaFuncSetAttribute.  One instance per kernel instantiation; remembers the largest
+// size configured on each device (relaxed atomics: racing host threads at worst repeat an idempotent call).
+struct SmemOptIn {
+  static constexpr int kMaxDevices = 64;
+  unsigned long long per_dev[kMaxDevices] = {};
+  template <typename K>
+  cudaError_t ensure(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if ((unsigned long long)bytes <= __atomic_load_n(&per_dev[dev], __ATOMIC_RELAXED)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    unsigned long long cur = __atomic_load_n(&per_dev[dev], __ATOMIC_RELAXED);
+    while (cur < bytes && !__atomic_compare_exchange_n(&per_dev[dev], &cur, (unsigned long long)bytes, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return cudaSuccess;
+  }
+};
+
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p) {

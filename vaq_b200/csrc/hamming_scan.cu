@@ -154,11 +154,10 @@ __global__ void __launch_bounds__(256, (W <= 2 ? 4 : 2)) ham_scan_kernel(const _
 
 template <int W, int QT>
 static cudaError_t launch_wq(const HamScanArgs &a, int threads, size_t smem_bytes, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem_bytes > 48 * 1024 && smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(ham_scan_kernel<W, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = optin.ensure(ham_scan_kernel<W, QT>, smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = smem_bytes;
   }
   dim3 grid((unsigned)a.splits, (unsigned)((a.nq + QT - 1) / QT));
   ham_scan_kernel<W, QT><<<grid, threads, smem_bytes, st>>>(a);

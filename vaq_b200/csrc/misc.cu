@@ -55,11 +55,10 @@ cudaError_t launch_refine(const float *xtrain, int64_t n, int D, const float *qu
                           cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   const size_t smem = (size_t)refine_num * sizeof(uint64_t);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = optin.ensure(refine_kernel, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   refine_kernel<<<nq, 256, smem, st>>>(xtrain, n, D, queries, in_labels, refine_num, k, labels, dists);
   return cudaGetLastError();
@@ -119,11 +118,10 @@ cudaError_t launch_rank_clusters(const float *q_proj, int nq, int D, const float
                                  int32_t *n_ranges, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   const size_t smem = (size_t)C * 8;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(rank_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = optin.ensure(rank_clusters_kernel, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   rank_clusters_kernel<<<nq, 256, smem, st>>>(q_proj, D, clusters, C, segdims, start, size, visit, k, ranges, n_ranges);
   return cudaGetLastError();

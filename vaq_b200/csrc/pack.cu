@@ -170,11 +170,10 @@ cudaError_t launch_encode(const float *x_proj, int64_t n, const float *centroids
   const int L = plan.L;
   const int chunk = kEncChunkFloats / L > 0 ? kEncChunkFloats / L : 1;
   const size_t smem = ((size_t)L * kEncRows + (size_t)chunk * L) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = optin.ensure(encode_kernel, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   dim3 grid((unsigned)((n + kEncRows - 1) / kEncRows), (unsigned)plan.M);
   encode_kernel<<<grid, kEncRows, smem, st>>>(x_proj, n, plan.M * plan.L, centroids, plan, codes);

@@ -47,7 +47,7 @@ __device__ __forceinline__ void emit(const MergeArgs &a, int q, int slot, uint64
 }
 
 __global__ void merge_level_kernel(const __grid_constant__ MergeArgs a) {
-  const int q = blockIdx.y, g = blockIdx.x;
+  const int q = blockIdx.x, g = blockIdx.y;      // queries on grid.x: no 65535 limit on the batch
   const int l0 = g * a.fan, l1 = min(a.G, l0 + a.fan);
   const int nl = l1 - l0, k = a.k;
   const uint64_t *base = a.in + (size_t)q * a.stride_q;
@@ -113,7 +113,7 @@ cudaError_t launch_merge_keys(const uint64_t *keys_in, int64_t stride_l, int64_t
       a.mid = buf[which];
     }
     const int threads = (k * min(G, kFan) >= 256) ? 256 : 64;
-    merge_level_kernel<<<dim3((unsigned)Gp, (unsigned)nq), threads, 0, st>>>(a);
+    merge_level_kernel<<<dim3((unsigned)nq, (unsigned)Gp), threads, 0, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || a.final_level) return e;
     in = a.mid; sl = k; sq = (int64_t)Gp * k; G = Gp; which ^= 1;

@@ -164,6 +164,14 @@ cudaError_t grow_codes(uint4 **codes, int64_t *cap_rows, int64_t n_rows, int W, 
   return cudaSuccess;
 }
 
+// TI state describes exactly the rows that were there when vaqgpu_set_clusters ran: appending rows drops it
+// (a TI search must never silently skip the new rows), and so does a failed vaqgpu_set_clusters.
+void clear_clusters(vaqgpu_index *h) {
+  cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_id_map);
+  h->d_clusters = nullptr; h->d_cl_start = h->d_cl_size = nullptr; h->d_id_map = nullptr;
+  h->C = 0; h->segdims = 0;
+}
+
 // Field placement inside the packed row + LUT placement (shared-memory resident vs spilled).
 int plan_model(vaqgpu_index *h) {
   const int M = h->M;
@@ -242,6 +250,29 @@ size_t scan_smem_bytes(int smem_lut_floats, int k, int threads) {
   return b;
 }
 
+// Row chunks per query tile for the filter kernels (grid = query tiles x chunks, one CTA per SM): enough CTAs to
+// fill the machine ~3x when there are few query tiles, every warp left with >= 16 tiles, chunks of at most 1M rows
+// so that all query tiles sweep a chunk while it is L2-resident — and, when the grid is only a few waves long, the
+// count in [c, 4c/3] whose last wave is fullest (CTAs come in multiples of the SM count).
+int64_t choose_chunks(int64_t n_tiles, int qtiles, int nwarps, int num_sms) {
+  const int64_t target = (int64_t)num_sms * 3;
+  const int64_t cap = std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16));
+  int64_t c = std::max<int64_t>(1, (target + qtiles - 1) / qtiles);
+  c = std::min(c, cap);
+  c = std::max<int64_t>(c, (n_tiles + 32767) / 32768);
+  if (c * qtiles <= 16ll * num_sms && c > 1) {
+    double best = 0.0;
+    int64_t pick = c;
+    for (int64_t t = c; t <= std::min(cap, c + c / 3 + 1); t++) {
+      const int64_t ctas = t * qtiles, waves = (ctas + num_sms - 1) / num_sms;
+      const double eff = (double)ctas / (double)(waves * num_sms);
+      if (eff > best + 1e-9) { best = eff; pick = t; }
+    }
+    c = pick;
+  }
+  return c;
+}
+
 int ensure_stream(cudaStream_t *st, cudaEvent_t *ev, int nev) {
   if (!*st) CU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
   for (int i = 0; i < nev; i++)
@@ -275,10 +306,10 @@ int tune_knob(const char *name, int dflt) {
 // The whole device-side search; exactly one of (d_labels,d_dists) / d_keys is the output.
 //
 // Scan kernel selection (the reference dispatches TI -> EA -> HEAP, VAQ.cpp:799-840):
-//   EA (default)     -> adc_filter_scan_kernel: stage-1 filter on the first group + exact stage 2
-//   HEAP             -> adc_scan_kernel without abandoning (exhaustive, as searchHeap)
+//   EA / HEAP        -> adc_filter16_scan_kernel (fp16 lower-bound filter + exact scoring of the survivors), or
+//                       adc_filter_scan_kernel when eight queries' fp16 tables do not fit in shared memory
 //   TI / visit       -> adc_scan_kernel over per-query row ranges, with abandoning
-//   VAQGPU_SCAN_V1   -> force adc_scan_kernel (lane-per-row, warp-uniform abandoning)
+//   VAQGPU_SCAN_V1   -> force adc_scan_kernel (lane-per-row; exhaustive with HEAP, warp-uniform abandoning with EA)
 int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, uint32_t flags, int32_t *d_labels,
                        float *d_dists, uint64_t *d_keys, cudaStream_t st, bool record) {
   if (nq < 0 || k <= 0) return fail(VAQGPU_EINVAL, "nq=%d k=%d", nq, k);
@@ -289,7 +320,9 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   const bool ti = (flags & VAQGPU_TI) != 0;
   if (ti && !h->d_clusters) return fail(VAQGPU_ESTATE, "VAQGPU_TI needs vaqgpu_set_clusters");
   const bool ea = (flags & VAQGPU_EA) != 0 || ti || !(flags & VAQGPU_HEAP);
-  const bool filter = ea && !ti && !(flags & VAQGPU_SCAN_V1) && h->n_rows > 0;
+  // HEAP (exhaustive) and EA return the same k best rows (VAQ.cpp:1718 vs :1750: same strict test, EA only skips
+  // rows that cannot pass it), so both run the filter kernels; VAQGPU_SCAN_V1 keeps the literal exhaustive loop.
+  const bool filter = !ti && !(flags & VAQGPU_SCAN_V1) && h->n_rows > 0;
   const bool want_sqrt = (flags & VAQGPU_SQRT) != 0;
   int launches = 0;
 
@@ -309,7 +342,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   int32_t res_floats = 0, spill_floats = 0;
 
   // ---- fp16 lower-bound tables, query tiles of 8 (default when eight queries' tables fit) -------------
-  bool filter16 = filter && !(flags & VAQGPU_SCAN_F32) && nq >= tune_knob("min16", 5);
+  bool filter16 = filter && !(flags & VAQGPU_SCAN_F32) && nq >= tune_knob("min16", 1);
   if (filter16) {
     apply_residency(h, (size_t)1 << 30, 8, lay, plan, res_floats, spill_floats);      // everything resident
     if (adc_filter16_smem_bytes(plan.row_stride, k, 1024) > kSmemCap) filter16 = false;
@@ -324,11 +357,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     int qb_max = (int)std::max<size_t>(T, std::min<size_t>((size_t)nq, kLutWorkspaceBytes / bytes_per_q));
     qb_max = (qb_max + T - 1) / T * T;
     const int qtiles_first = (std::min(nq, qb_max) + T - 1) / T;
-    const int64_t target = (int64_t)h->num_sms * 3;
-    int64_t n_chunks = std::max<int64_t>(1, (target + qtiles_first - 1) / qtiles_first);
-    n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16)));
-    n_chunks = std::max<int64_t>(n_chunks, (n_tiles + 32767) / 32768);          // <= 1M rows per chunk
-    n_chunks = tune_knob("chunks", (int)n_chunks);
+    int64_t n_chunks = tune_knob("chunks", (int)choose_chunks(n_tiles, qtiles_first, nwarps, h->num_sms));
     const int64_t chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
     n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     if (n_chunks > 65535) return fail(VAQGPU_EINVAL, "index too large for one launch (%lld chunks)", (long long)n_chunks);
@@ -414,11 +443,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     // ---- row chunks: enough CTAs to fill the machine, chunks small enough to stay L2-resident while
     // every query tile sweeps them (query tiles are the fast grid dimension)
     const int qtiles_first = (std::min(nq, qb_max) + T - 1) / T;
-    const int64_t target = (int64_t)h->num_sms * 3;
-    int64_t n_chunks = std::max<int64_t>(1, (target + qtiles_first - 1) / qtiles_first);
-    n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16)));
-    n_chunks = std::max<int64_t>(n_chunks, (n_tiles + 32767) / 32768);          // <= 1M rows per chunk
-    n_chunks = tune_knob("chunks", (int)n_chunks);
+    int64_t n_chunks = tune_knob("chunks", (int)choose_chunks(n_tiles, qtiles_first, nwarps, h->num_sms));
     int64_t chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
     n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
     if (n_chunks > 65535) return fail(VAQGPU_EINVAL, "index too large for one launch (%lld chunks)", (long long)n_chunks);
@@ -474,7 +499,8 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   CU(adc_scan_occupancy(lay.W, threads, smem, &ctas_per_sm));
   if (ctas_per_sm < 1) return fail(VAQGPU_ECUDA, "ADC scan kernel does not fit an SM with %zu B shared memory", smem);
   const int nwarps = threads / 32;
-  const int qb_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)nq, kLutWorkspaceBytes / ((size_t)plan.row_stride * 4)));
+  // grid.y of adc_scan_kernel is the query: at most 65535 per launch
+  const int qb_max = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nq, kLutWorkspaceBytes / ((size_t)plan.row_stride * 4), (size_t)65535}));
   // CTAs per query: fill ~2 waves of the machine when there are few queries, but leave each
   // warp at least 8 tiles so the per-CTA LUT staging stays amortised.
   const int64_t target = (int64_t)h->num_sms * ctas_per_sm * 2;
@@ -658,6 +684,7 @@ int vaqgpu_add_codes_u16(vaqgpu_t *h, const uint16_t *codes, int64_t n) {
   if (n == 0) return VAQGPU_OK;
   if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index (labels are int32, utils/Types.hpp:100)");
   DeviceGuard g(h->device);
+  if (h->C) clear_clusters(h);
   CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
   const int64_t chunk = std::min<int64_t>(n, kStageRows);
   CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
@@ -677,6 +704,7 @@ int vaqgpu_encode_add(vaqgpu_t *h, const float *x_proj, int64_t n) {
   if (n == 0) return VAQGPU_OK;
   if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index");
   DeviceGuard g(h->device);
+  if (h->C) clear_clusters(h);
   CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
   const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t)(256ull << 20) / (h->D * 4)));
   CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
@@ -698,6 +726,7 @@ int vaqgpu_add_codes_synthetic(vaqgpu_t *h, int64_t n, uint64_t seed, const floa
   if (n == 0) return VAQGPU_OK;
   if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index");
   DeviceGuard g(h->device);
+  if (h->C) clear_clusters(h);
   CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
   const float *d_cdf = nullptr;
   if (cdf) {
@@ -812,17 +841,18 @@ int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t s
     if (start[c] < 0 || size[c] < 0 || start[c] + size[c] > h->n_rows)
       return fail(VAQGPU_EINVAL, "cluster %d range [%lld,+%lld) outside the index (%lld rows)", c, (long long)start[c], (long long)size[c], (long long)h->n_rows);
   DeviceGuard g(h->device);
-  cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_id_map);
-  h->d_clusters = nullptr; h->d_cl_start = h->d_cl_size = nullptr; h->d_id_map = nullptr;
-  CU(cudaMalloc(&h->d_clusters, (size_t)C * segdims * sizeof(float)));
-  CU(cudaMemcpy(h->d_clusters, clusters, (size_t)C * segdims * sizeof(float), cudaMemcpyHostToDevice));
-  CU(cudaMalloc(&h->d_cl_start, (size_t)C * sizeof(int64_t)));
-  CU(cudaMemcpy(h->d_cl_start, start, (size_t)C * sizeof(int64_t), cudaMemcpyHostToDevice));
-  CU(cudaMalloc(&h->d_cl_size, (size_t)C * sizeof(int64_t)));
-  CU(cudaMemcpy(h->d_cl_size, size, (size_t)C * sizeof(int64_t), cudaMemcpyHostToDevice));
-  if (id_map) {
-    CU(cudaMalloc(&h->d_id_map, (size_t)h->n_rows * sizeof(int32_t)));
-    CU(cudaMemcpy(h->d_id_map, id_map, (size_t)h->n_rows * sizeof(int32_t), cudaMemcpyHostToDevice));
+  clear_clusters(h);
+  auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, bytes);
+    return e != cudaSuccess ? e : cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  cudaError_t e = up((void **)&h->d_clusters, clusters, (size_t)C * segdims * sizeof(float));
+  if (e == cudaSuccess) e = up((void **)&h->d_cl_start, start, (size_t)C * sizeof(int64_t));
+  if (e == cudaSuccess) e = up((void **)&h->d_cl_size, size, (size_t)C * sizeof(int64_t));
+  if (e == cudaSuccess && id_map) e = up((void **)&h->d_id_map, id_map, (size_t)h->n_rows * sizeof(int32_t));
+  if (e != cudaSuccess) {
+    clear_clusters(h);
+    return fail(e == cudaErrorMemoryAllocation ? VAQGPU_ENOMEM : VAQGPU_ECUDA, "vaqgpu_set_clusters: %s", cudaGetErrorString(e));
   }
   h->C = C; h->segdims = segdims;
   return VAQGPU_OK;
@@ -989,23 +1019,28 @@ int ham_query_impl(hamgpu_index *h, const uint64_t *d_queries, int nq, int k, in
   const size_t smem = (size_t)qt * W * 16 + ((size_t)nwarps * qt * k + k + qt) * sizeof(uint64_t);
   if (smem > kSmemCap) return fail(VAQGPU_EINVAL, "k=%d needs %zu B shared memory", k, smem);
   const int64_t n_tiles = (h->n_rows + kTileRows - 1) / kTileRows;
-  const int qgroups = (nq + qt - 1) / qt;
+  const int qb_max = std::min(nq, 32768);                       // grid.y = query groups: bounded per launch
+  const int qgroups = (qb_max + qt - 1) / qt;
   const int64_t target = (int64_t)h->num_sms * 4 * 2;
   int splits = (int)std::max<int64_t>(1, (target + qgroups - 1) / qgroups);
   splits = (int)std::min<int64_t>(splits, std::max<int64_t>(1, n_tiles / (nwarps * 8)));
-  CU(h->w_keys.ensure((size_t)nq * splits * k * sizeof(uint64_t)));
-  if (splits > 16) CU(h->w_scratch.ensure((size_t)2 * nq * ((splits + 15) / 16) * k * sizeof(uint64_t)));
+  CU(h->w_keys.ensure((size_t)qb_max * splits * k * sizeof(uint64_t)));
+  if (splits > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((splits + 15) / 16) * k * sizeof(uint64_t)));
   CU(cudaEventRecord(h->ev[0], st));
-  HamScanArgs a{};
-  a.codes = h->d_codes; a.n_rows = h->n_rows; a.W = W; a.queries = dq;
-  a.nq = nq; a.k = k; a.splits = splits; a.qt = qt;
-  a.out_keys = (uint64_t *)h->w_keys.p;
-  CU(launch_ham_scan(a, threads, smem, st));
-  launches++;
-  CU(cudaEventRecord(h->ev[1], st));
-  CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)splits * k, splits, nq, k, 0, 1, d_idx, d_dist, d_keys, nullptr,
-                       h->id_base, (uint64_t *)h->w_scratch.p, st));
-  launches += splits > 16 ? 2 : 1;
+  for (int q0 = 0; q0 < nq; q0 += qb_max) {
+    const int qb = std::min(qb_max, nq - q0);
+    HamScanArgs a{};
+    a.codes = h->d_codes; a.n_rows = h->n_rows; a.W = W; a.queries = dq + (size_t)q0 * W;
+    a.nq = qb; a.k = k; a.splits = splits; a.qt = qt;
+    a.out_keys = (uint64_t *)h->w_keys.p;
+    CU(launch_ham_scan(a, threads, smem, st));
+    launches++;
+    if (q0 + qb >= nq) CU(cudaEventRecord(h->ev[1], st));
+    CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)splits * k, splits, qb, k, 0, 1, d_idx ? d_idx + (size_t)q0 * k : nullptr,
+                         d_dist ? d_dist + (size_t)q0 * k : nullptr, d_keys ? d_keys + (size_t)q0 * k : nullptr, nullptr,
+                         h->id_base, (uint64_t *)h->w_scratch.p, st));
+    launches += splits > 16 ? 2 : 1;
+  }
   CU(cudaEventRecord(h->ev[2], st));
   h->timed = true;
   h->cfg[0] = threads; h->cfg[1] = splits; h->cfg[2] = qt; h->cfg[3] = 0; h->cfg[4] = (int32_t)smem; h->cfg[5] = W;

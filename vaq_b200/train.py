@@ -220,25 +220,3 @@ def train(X: np.ndarray, budget: int, M: int, min_bits: int, max_bits: int, *, p
     model = VAQModel(L=L, bits=bits, centroids=cents, eig=eig, var_per_subs=var_subs)
     return model, XP
 
-
-def encode_host(model: VAQModel, XP: np.ndarray, block: int = 1 << 16) -> np.ndarray:
-    """Host encode (reference VAQ::encodeImpl, VAQ.cpp:728-748): nearest centroid per
-    (row, subspace), lowest code on ties.  Evaluates the distances directly
-    (``sum_j (x_j - c_j)^2``, float32) so that it agrees with the reference up to float
-    near-ties; the bit-exact device path is vaq_b200's encode kernel."""
-    XP = np.ascontiguousarray(XP, np.float32)
-    n = XP.shape[0]
-    codes = np.empty((n, model.M), np.uint16)
-    L = model.L
-    for s in range(model.M):
-        C = model.centroids[s]
-        K = C.shape[0]
-        blk = max(1, min(block, (1 << 25) // (K * L)))
-        for b in range(0, n, blk):
-            x = XP[b:b + blk, s * L:(s + 1) * L]
-            d = np.zeros((x.shape[0], K), np.float32)
-            for j in range(L):
-                t = x[:, j:j + 1] - C[None, :, j]
-                d += t * t
-            codes[b:b + blk, s] = d.argmin(1).astype(np.uint16)
-    return codes

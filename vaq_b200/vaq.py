@@ -39,6 +39,7 @@ class VAQ:
         self.model: host_train.VAQModel | None = None
         self.index: VAQIndex | None = None
         self._ti = None
+        self._raw_key, self._raw_keepalive = None, None
 
     # VAQ::parseMethodString, VAQ.cpp:1189-1267
     def parseMethodString(self, s: str) -> None:
@@ -78,6 +79,11 @@ class VAQ:
         m = self.model
         self.index = VAQIndex(m.L, m.bits, m.centroids, eig=m.eig, device=self.device)
         self._ti = None
+        self.reset_raw_cache()
+
+    def reset_raw_cache(self) -> None:
+        """Forget which raw vectors are resident on the device (refine() uploads them again)."""
+        self._raw_key, self._raw_keepalive = None, None
 
     # VAQ::encode, VAQ.cpp:663-774 (device; rows already projected)
     def encode(self, XTrainProjected: np.ndarray) -> None:
@@ -131,9 +137,13 @@ class VAQ:
 
     # VAQ::refine, VAQ.cpp:849-876
     def refine(self, XTest: np.ndarray, answersIn: LabelDistVecF, XTrain: np.ndarray, k: int) -> LabelDistVecF:
-        if getattr(self, "_raw_id", None) != id(XTrain):
-            self.index.set_raw_vectors(XTrain)
-            self._raw_id = id(XTrain)
+        # raw rows are uploaded once per (buffer, shape); a new index, a different array or reset_raw_cache() re-uploads.
+        # (An array mutated in place keeps its key: call reset_raw_cache() after changing XTrain's contents.)
+        X = np.ascontiguousarray(XTrain, np.float32)
+        key = (X.ctypes.data, X.shape, X.strides)
+        if self._raw_key != key:
+            self.index.set_raw_vectors(X)
+            self._raw_key, self._raw_keepalive = key, X          # the address stays ours while it is the cache key
         lab, dis = self.index.refine(XTest, answersIn.labels, k)
         return LabelDistVecF(lab, dis)
 
