@@ -4,19 +4,28 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU search
 
-Workload (BASELINE.json configs[1]): SIFT1M-shape synthetic, 1M x 128 base, 10K queries,
-VAQ 256-bit budget over 32 subspaces, k = 10.  A step = one search of the whole 10K-query batch
-against the index.  N > 1 (torchrun, one rank per GPU): the code matrix is row-sharded, every
-rank scans its rows for all queries, one NCCL all-gather of the shard-local top-k + device merge
-(strong scaling: total rows fixed).
+Default workload (BASELINE.json configs[1]): SIFT1M-shape synthetic, 1M x 128 base, 10K queries, VAQ 256-bit budget
+over 32 subspaces, k = 10.  A step = one search of the whole query batch against the index.  `--workload` selects
+the other BASELINE shapes (siftsmall C1, GIST1M C3 spill path, Deep100M C4, 1B C5).
+
+N > 1 (torchrun, one rank per GPU): the packed code matrix is ROW-SHARDED over the N GPUs (rank r holds rows
+[r*ceil(n/N), (r+1)*ceil(n/N))), every rank scans its rows for all queries while the shards exchange their running
+k-th-best bounds through NVLink peer memory, then one NCCL all-gather of the shard-local top-k key lists + a device
+merge.  Strong scaling: total rows and queries fixed.  (`--row-shards R` < N is an experiment knob: N/R replica
+groups of R row shards that split the query batch.)
 
 One JSON line on stdout (rank 0); everything else goes to stderr.
 """
 from __future__ import annotations
 
+import os
+
+if "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # torchrun exports OMP_NUM_THREADS=1; the host-side problem set-up (numpy) may use this rank's share of the cores
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["WORLD_SIZE"])))
+
 import argparse
 import json
-import os
 import subprocess
 import sys
 import threading
@@ -28,15 +37,36 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+# source "vectors": base vectors generated on the host and encoded on the device (VAQ::encode semantics);
+# source "codes": model trained on a host sample, rows generated directly on the device from the sample's per-subspace
+#                 code distribution (the 100M / 1B-row shapes no host can hold), regenerated on the host
+#                 (vaq_b200/synth.py) for any row range the checks need.
 WORKLOADS = {
-    # name: rows, dims, budget, M, min_bits, max_bits, queries, k, decay
-    "sift1m_256b_m32_k10": dict(n=1_000_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0),
-    "small_256b_m32_k10": dict(n=100_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=1_000, k=10, decay=4.0),
-    "shard125k_256b_m32_k10": dict(n=125_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0),
-    "tiny16k_256b_m32_k10": dict(n=16_384, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0),
+    "sift1m_256b_m32_k10": dict(n=1_000_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0,
+                                source="vectors", desc="BASELINE configs[1] (C2): SIFT1M-shape 1M x 128, 10K queries, VAQ 256-bit m32, k=10"),
+    "siftsmall_128b_m16_k100": dict(n=10_000, d=128, budget=128, M=16, min_bits=6, max_bits=10, nq=100, k=100, decay=4.0,
+                                    source="vectors", sift=True, train_rows=10_000,
+                                    desc="BASELINE configs[0] (C1): siftsmall-shape 10K x 128, the reference's 100 shipped queries, VAQ 128-bit, k=100"),
+    "sift1m_256b_m32_min2max13_k10": dict(n=1_000_000, d=128, budget=256, M=32, min_bits=2, max_bits=13, nq=10_000, k=10, decay=4.0,
+                                          source="vectors",
+                                          desc="the reference's own SIFT1M setting (ExperimentsParameters.txt:55: 256 bit, 32 segments, min 2 / max 13 bits)"),
+    "gist1m_512b_m64_k10": dict(n=1_000_000, d=960, budget=512, M=64, min_bits=4, max_bits=13, nq=1_000, k=10, decay=15.0,
+                                source="codes", train_rows=20_000,
+                                desc="BASELINE configs[2] (C3): GIST1M-shape 1M x 960, 1K queries, VAQ 512-bit m64 min4/max13 (large-LUT spill path)"),
+    "deep100m_128b_m16_k10": dict(n=100_000_000, d=96, budget=128, M=16, min_bits=6, max_bits=10, nq=10_000, k=10, decay=4.0,
+                                  source="codes", desc="BASELINE configs[3] (C4): Deep100M-shape 100M x 96, 10K queries, VAQ 128-bit m16"),
+    "synth1b_256b_m32_k10": dict(n=1_000_000_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=1_000, k=10, decay=4.0,
+                                 source="codes", ham_rows=1_000_000_000,
+                                 desc="BASELINE configs[4] (C5): 1B x 128, VAQ 256-bit m32, 1K queries per step + 1B x 256-bit Hamming scan"),
+    # development shapes
+    "small_256b_m32_k10": dict(n=100_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=1_000, k=10, decay=4.0, source="vectors",
+                               desc="development"),
+    "shard125k_256b_m32_k10": dict(n=125_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0, source="vectors",
+                                   desc="development: one of eight row shards of the SIFT1M shape"),
 }
 TRAIN_ROWS = 32768
 SEED = 13517106
+FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 lanes x 2 flop x 1.965 GHz
 
 
 def log(*a):
@@ -65,17 +95,47 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
-def build_problem(w: dict):
+class Problem:
     """Seeded synthetic base/queries + host-trained model (the reference keeps training on the host)."""
-    from vaq_b200 import synth, train
-    t0 = time.time()
-    X = synth.decaying_gaussian(w["n"], w["d"], decay=w["decay"], seed=SEED)
-    Qraw = synth.decaying_gaussian(w["nq"], w["d"], decay=w["decay"], seed=SEED + 7)
-    model, _ = train.train(X[:TRAIN_ROWS], w["budget"], w["M"], w["min_bits"], w["max_bits"], kmeans_iters=8, seed=SEED)
-    XP = model.project(X)
-    Q = model.project(Qraw)
-    log(f"[bench] problem built in {time.time() - t0:.1f}s bits={model.bits.tolist()}")
-    return model, X, XP, Qraw, Q
+
+    def __init__(self, w: dict, need_vectors: bool = True):
+        from vaq_b200 import io as vio
+        from vaq_b200 import synth, train
+        t0 = time.time()
+        self.w = w
+        self.n, self.nq, self.k = w["n"], w["nq"], w["k"]
+        train_rows = w.get("train_rows", TRAIN_ROWS)
+        gen = (lambda n, seed: synth.sift_like(n, w["d"], seed=seed)) if w.get("sift") else \
+              (lambda n, seed: synth.decaying_gaussian(n, w["d"], decay=w["decay"], seed=seed))
+        self.X = self.XP = None
+        if w["source"] == "vectors":
+            self.X = gen(self.n, SEED)
+            Xtrain = self.X[:train_rows]
+        else:
+            Xtrain = gen(train_rows, SEED)
+        qfix = ROOT / "tests" / "golden" / "siftsmall_query.fvecs"
+        if w.get("sift") and qfix.exists():
+            self.Qraw = vio.read_fvecs(qfix)[: self.nq]          # the reference's shipped siftsmall queries (fixture)
+        else:
+            self.Qraw = gen(self.nq, SEED + 7)
+        self.model, XPtrain = train.train(Xtrain, w["budget"], w["M"], w["min_bits"], w["max_bits"], kmeans_iters=8, seed=SEED)
+        self.Q = self.model.project(self.Qraw)
+        self.cdf = None
+        if w["source"] == "vectors":
+            if need_vectors:
+                self.XP = self.model.project(self.X)
+        else:
+            self.XPtrain = XPtrain
+        log(f"[bench] problem built in {time.time() - t0:.1f}s bits={self.model.bits.tolist()}")
+
+    def make_cdf(self, sample_codes):
+        from vaq_b200 import synth
+        self.cdf = synth.code_cdf(sample_codes, self.model.bits)
+
+    def host_codes(self, row0: int, n: int) -> np.ndarray:
+        """codes of global rows [row0, row0+n) of a "codes" workload, regenerated on the host"""
+        from vaq_b200 import synth
+        return synth.synth_codes(self.model.bits, n, row0, SEED, self.cdf)
 
 
 class ClockSampler:
@@ -134,13 +194,33 @@ def measured_peak_hbm() -> tuple[float, str]:
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
+def ncu_traffic(kernel: str, workload: str, n_gpus: int):
+    """DRAM bytes per launch of `kernel` on `workload` from the committed ncu --set full captures (profiles/ncu_traffic.json)."""
+    try:
+        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        for ent in tj.get(kernel, []) if isinstance(tj.get(kernel), list) else [tj.get(kernel, {})]:
+            if ent.get("workload") == workload and ent.get("n_gpus", 1) == n_gpus:
+                return ent.get("dram_bytes_read", 0) + ent.get("dram_bytes_write", 0)
+    except Exception:
+        pass
+    return None
+
+
+def use_host_threads(n: int):
+    try:        # torchrun exports OMP_NUM_THREADS=1; the CPU checkers may use the idle host cores
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(max(1, n))
+    except OSError:
+        pass
+
+
 # ---------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU search (compiled unmodified reference when available)
 # ---------------------------------------------------------------------------------------------
 
 def cpu_reference_search(model, codes, Q, k, seconds_target: float, threads: int):
-    """Times reference VAQ::search (EA mode, the reference's fastest exact mode) on a bounded sample of
-    the query batch.  Returns (qps, n_queries, kind, labels, dists)."""
+    """Times reference VAQ::search (EA mode, the reference's fastest exact mode) on a bounded sample of the query
+    batch against `codes`.  Returns (qps, n_queries, kind, labels, dists, seconds)."""
     from oracle import oracle as orc
     om = orc.Model(model.L, model.bits, model.centroids)
     if orc.Ref.available():
@@ -169,44 +249,62 @@ def cpu_reference_search(model, codes, Q, k, seconds_target: float, threads: int
     return n / dt, n, kind, lab, dis, dt
 
 
+def reference_codes(pb: Problem, max_rows: int):
+    """(codes, rows_used, how) for the CPU arm: the whole matrix encoded by the reference itself for "vectors"
+    workloads, a host-regenerated row slice for "codes" workloads."""
+    from oracle import oracle as orc
+    om = orc.Model(pb.model.L, pb.model.bits, pb.model.centroids)
+    if pb.w["source"] == "vectors":
+        t0 = time.time()
+        if orc.Ref.available():      # VAQ::encode of the compiled reference (OpenMP over rows, VAQ.cpp:733)
+            rv = orc.Ref().vaq(om, orc.NN_EA)
+            codes = rv.encode(pb.XP)
+            rv.close()
+        else:
+            codes = orc.Port().encode(om, pb.XP)
+        log(f"[bench] host encode {time.time() - t0:.1f}s")
+        return codes, pb.n, "all rows"
+    if pb.cdf is None:
+        pb.make_cdf(orc.Port().encode(om, pb.XPtrain))
+    rows = min(pb.n, max_rows)
+    return pb.host_codes(0, rows), rows, f"rows [0,{rows}) of {pb.n} (QPS scaled linearly by {rows}/{pb.n})"
+
+
 def run_reference_arm(args, w, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
-    model, X, XP, Qraw, Q = build_problem(w)
-    om = orc.Model(model.L, model.bits, model.centroids)
-    t0 = time.time()
-    if orc.Ref.available():      # VAQ::encode of the compiled reference (OpenMP over rows, VAQ.cpp:733)
-        rv = orc.Ref().vaq(om, orc.NN_EA)
-        codes = rv.encode(XP)
-        rv.close()
-    else:
-        codes = orc.Port().encode(om, XP)
-    log(f"[bench] host encode {time.time() - t0:.1f}s")
+    pb = Problem(w)
     threads = os.cpu_count() or 1
+    use_host_threads(threads)
+    codes, rows_used, how = reference_codes(pb, args.cpu_rows)
+    scale = rows_used / pb.n
     vals = []
     n_used = 0
     kind = "reference"
     per_step_target = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     for it in range(args.warmup + args.steps):
-        qps, n_used, kind, _, _, dt = cpu_reference_search(model, codes, Q, w["k"], per_step_target, threads)
+        qps, n_used, kind, _, _, dt = cpu_reference_search(pb.model, codes, pb.Q, pb.k, per_step_target, threads)
         if it >= args.warmup:
-            vals.append((qps, dt))
+            vals.append((qps * scale, dt))
     qps = float(np.mean([v[0] for v in vals]))
     ms = float(np.mean([v[1] for v in vals]) * 1e3)
     line = {
         "impl": "reference", "metric": "queries/sec at recall@10", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "rows": w["n"], "dims": w["d"], "queries": w["nq"], "k": w["k"], "bits": w["budget"],
-                   "subspaces": w["M"], "mode": "EA (VAQ::searchEarlyAbandon)"},
+        "config": workload_config(name, w, "EA (VAQ::searchEarlyAbandon)"),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind,
-                         "sample": f"{n_used} of {w['nq']} queries per step, all {w['n']} rows, query-sliced over {threads} threads"},
+                         "sample": f"{n_used} of {w['nq']} queries per step, {how}, query-sliced over {threads} threads"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def workload_config(name, w, mode):
+    return {"workload": name, "rows": w["n"], "dims": w["d"], "queries": w["nq"], "k": w["k"], "bits": w["budget"],
+            "subspaces": w["M"], "mode": mode}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -217,8 +315,8 @@ def run_gpu_arm(args, w, name):
     import torch
     import torch.distributed as dist
     from vaq_b200 import synth
-    from vaq_b200.index import EA, PROJECTED, VAQIndex
-    from vaq_b200.sharded import ShardedVAQ, shard_bounds
+    from vaq_b200.index import EA, PROJECTED, HammingIndex, VAQIndex
+    from vaq_b200.sharded import ShardedHamming, ShardedVAQ
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,34 +328,32 @@ def run_gpu_arm(args, w, name):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
-    model, X, XP, Qraw, Q = build_problem(w)
-    n, nq, k = w["n"], w["nq"], w["k"]
+    pb = Problem(w)
+    model, Q = pb.model, pb.Q
+    n, nq, k = pb.n, pb.nq, pb.k
     flags = EA | PROJECTED | (0x1000 if args.scan_v1 else 0)
 
-    # index: this rank's row block, encoded on the device (bit-exact vs the oracle, tests/test_gpu_vaq.py)
-    # Layout.  --row-shards R: R ranks share one copy of the code matrix (row-sharded), world/R replica groups split
-    # the query batch.  Default ("auto"): the fewest row shards that keep a GPU's share of the packed matrix under
-    # 16 GiB — a 32 MB matrix is replicated, a 1B-row one is row-sharded.  The pure row-sharded layout BASELINE.json
-    # names (R = N) is always timed as well (`row_sharded_layout` in the JSON line).
-    packed_bytes = n * 16 * (-(-w["budget"] // 128))
-    R = args.row_shards
-    if not R:
-        R = 1
-        while R < world and packed_bytes / R > (16 << 30):
-            R *= 2
+    # ---- index: this rank's row block.  Default R = N: the pure row-sharded layout BASELINE.json names.
+    R = args.row_shards or world
     sh = ShardedVAQ(model.L, model.bits, model.centroids, model.eig, n, rank, world, local_rank, row_shards=R)
     t0 = time.time()
-    sh.index.encode_add(XP[sh.lo:sh.hi])
-    log(f"[bench] rank {rank}: encoded rows [{sh.lo},{sh.hi}) in {time.time() - t0:.1f}s; row_bytes={sh.index.row_bytes}")
+    if w["source"] == "vectors":
+        sh.index.encode_add(pb.XP[sh.lo:sh.hi])          # device encode (bit-exact vs VAQ::encode, checked below)
+    else:
+        # the training sample, encoded on the device, only shapes the synthetic code distribution
+        tmp = VAQIndex(model.L, model.bits, model.centroids, device=local_rank)
+        tmp.encode_add(pb.XPtrain)
+        pb.make_cdf(tmp.get_codes())
+        tmp.close()
+        sh.add_synthetic(SEED, pb.cdf)
+    torch.cuda.synchronize()
+    log(f"[bench] rank {rank}: rows [{sh.lo},{sh.hi}) resident in {time.time() - t0:.1f}s; row_bytes={sh.index.row_bytes}")
     ix = sh.index
-
-    sh_rows = None
-    if world > 1 and sh.R < world:
-        sh_rows = ShardedVAQ(model.L, model.bits, model.centroids, model.eig, n, rank, world, local_rank, row_shards=world)
-        sh_rows.index.encode_add(XP[sh_rows.lo:sh_rows.hi])
+    exchange = False
+    if world > 1 and not args.no_bound_exchange:
+        exchange = sh.enable_bound_exchange(nq)
 
     d_q = torch.from_numpy(Q).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -290,7 +386,7 @@ def run_gpu_arm(args, w, name):
         torch.cuda.synchronize()
         t = ix.last_timings()
         scan_ms.append(t["scan_ms"]); lut_ms.append(t["lut_ms"]); merge_ms.append(t["merge_ms"])
-        launches += ix.last_config()["launches"] + (1 if world > 1 else 0) + 1   # + all-gather + final merge
+        launches += ix.last_config()["launches"] + (1 if world > 1 else 0) + sh.qgroups   # + all-gather + final merge(s)
     barrier()
     clocks = sampler.stop() if sampler else None
     step_ms = np.array([a.elapsed_time(b) for a, b in ev], dtype=np.float64)
@@ -299,28 +395,11 @@ def run_gpu_arm(args, w, name):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = nq * args.steps / (total_ms / 1e3)
-
-    # ---- the same steps on the pure row-sharded layout (N shards, all queries on every rank), when it is not the default
-    row_layout = None
-    if sh_rows is not None:
-        for _ in range(args.warmup):
-            sh_rows.search(d_q, k, flags)
-        barrier()
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)
-            barrier()
-            ev2[i][0].record(st)
-            rl, rd = sh_rows.search(d_q, k, flags)
-            ev2[i][1].record(st)
-            torch.cuda.synchronize()
-        barrier()
-        t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        same = bool(torch.equal(rl, labels) and torch.equal(rd.view(torch.int32), dists.view(torch.int32)))
-        row_layout = {"sharding": f"rows/{world}", "value": nq * args.steps / (float(t2.item()) / 1e3), "unit": "queries/s",
-                      "ms_per_step": float(t2.item()) / args.steps, "identical_to_default_layout": same,
-                      "scan_ms": sh_rows.index.last_timings()["scan_ms"]}
+    scan_all = torch.tensor([float(np.mean(scan_ms)), float(np.mean(lut_ms)), float(np.mean(merge_ms))], dtype=torch.float64, device=dev)
+    scan_max = scan_all.clone()
+    if world > 1:
+        dist.all_reduce(scan_max, op=dist.ReduceOp.MAX)
+    scan_max = [float(x) for x in scan_max.cpu()]
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region
     q_pin = torch.from_numpy(Q).pin_memory()
@@ -349,13 +428,71 @@ def run_gpu_arm(args, w, name):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_qps = nq * args.steps / float(e2e_s.item())
 
+    peak, peak_src = measured_peak_hbm()
+
+    # ---- planted needles (device-generated workloads; collective): queries placed on the code tuple of known rows,
+    # one or more per shard, must return that row first with the oracle's distance (checked on rank 0 below)
+    needles = needle_q = needle_out = None
+    if w["source"] == "codes":
+        needles = [int((r + 0.37) * n / max(world, 8)) for r in range(max(world, 8))]
+        needle_q = np.stack([np.concatenate([model.centroids[s][c] for s, c in enumerate(pb.host_codes(p, 1)[0])])
+                             for p in needles]).astype(np.float32)
+        nl, nd = sh.search(torch.from_numpy(needle_q).to(dev), k, flags)
+        needle_out = (nl.cpu().numpy(), nd.cpu().numpy())
+
+    # ---- Hamming scan, row-sharded over the same ranks (collective: every rank takes part)
+    hamming_sharded = None
+    if not args.no_hamming:
+        try:
+            hn = int(w.get("ham_rows", args.ham_rows))
+            hs = ShardedHamming(256, hn, rank, world, local_rank)
+            hs.add_synthetic(SEED)
+            hq_n = args.ham_queries
+            # planted needles: query j is row p_j of the matrix with 3 bits flipped -> must come back first at distance 3
+            planted = (np.arange(min(8, hq_n), dtype=np.int64) * (hn // 8) + 12345) % hn
+            hq_host = synth.synth_bitvectors(hq_n, 10 ** 10, 256, SEED)
+            for j, p in enumerate(planted):
+                row = synth.synth_bitvectors(1, int(p), 256, SEED)[0]
+                row[0] ^= np.uint64(0b111)
+                hq_host[j] = row
+            hqv = torch.from_numpy(hq_host.view(np.int64)).to(dev)
+            hms = []
+            for i in range(3 + 5):
+                flush.fill_(i)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                hidx, hdist = hs.query(hqv, k)
+                e1.record(st)
+                torch.cuda.synchronize()
+                if i >= 3:
+                    hms.append(e0.elapsed_time(e1))
+            tm = torch.tensor([float(np.sum(hms))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            hscan = hs.index.last_timings()["scan_ms"]
+            hcfg = hs.index.last_config()
+            qt = max(1, hcfg["queries_per_cta"])
+            n_loc = hs.hi - hs.lo
+            hi_h, hd_h = hidx.cpu().numpy(), hdist.cpu().numpy()
+            needles_ok = bool(all(hi_h[j, 0] == planted[j] and hd_h[j, 0] == 3 for j in range(len(planted))))
+            hbytes = -(-hq_n // qt) * n_loc * 32
+            hamming_sharded = {"kernel": "ham_scan_kernel", "rows_total": hn, "rows_per_gpu": n_loc, "bits": 256, "queries": hq_n,
+                               "k": k, "sharding": f"rows/{world}", "qps": hq_n * 5 / (float(tm.item()) / 1e3),
+                               "ms_per_batch": float(tm.item()) / 5, "scan_ms_rank0": hscan, "queries_per_pass": qt,
+                               "achieved": hbytes / (hscan / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": hbytes / (hscan / 1e3) / 1e9 / peak, "planted_needles_ok": needles_ok}
+            hs.index.close()
+        except Exception as e:      # never hide the headline behind an auxiliary leg
+            hamming_sharded = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (ADC scan), T = 1 accounting (each query's CTAs stream the rows)
+    # ---- roofline of the dominant kernel (ADC scan): SURVEY 8d accounting
     cfg = ix.last_config()
     n_local = sh.hi - sh.lo
     qa, qb_ = sh.query_slice(nq)
@@ -364,41 +501,50 @@ def run_gpu_arm(args, w, name):
     lut_bytes = int(ix.lut_size) * 4
     n_launch = -(-nq_rank // cfg["queries_per_launch"])
     T = max(1, cfg["queries_per_cta"])
-    # SURVEY 8d: one pass over the local rows per query TILE (T queries share the stream) + per-query LUT and result bytes
+    # one pass over the local rows per query TILE (T queries share the stream) + per-query LUT and result bytes
     alg_bytes_step = -(-nq_rank // T) * n_local * row_bytes + nq_rank * (lut_bytes + k * 8 * cfg["row_chunks"])
     scan_ms_mean = float(np.mean(scan_ms))
-    peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes_step / (scan_ms_mean / 1e3) / 1e9
     kname = {1: "adc_scan_kernel", 2: "adc_filter_scan_kernel", 3: "adc_filter16_scan_kernel"}.get(cfg["scan_kernel"], "adc_scan_kernel")
-    traffic = None
-    try:        # DRAM bytes per launch of this kernel on this workload from the committed ncu --set full capture
-        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
-        ent = tj.get(kname, {})
-        if ent.get("workload") == name and ent.get("n_gpus") == world:
-            traffic = ent.get("dram_bytes_read", 0) + ent.get("dram_bytes_write", 0)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
-                "launch_ms": scan_ms_mean / n_launch, "query_tile_T": T,
+    l2_resident = n_local * row_bytes <= 100e6 and nq_rank > T
+    roofline = {"bound": "smem_lsu" if l2_resident else "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(kname, name, world), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_step / n_launch, "launch_ms": scan_ms_mean / n_launch, "query_tile_T": T,
                 "pairs_per_s": nq_rank * n_local / (scan_ms_mean / 1e3),
-                "note": ("SURVEY 8d accounting: ceil(nq/T) passes over the packed rows (T queries share each pass) + LUT/result bytes; "
-                         f"at this shape the packed codes ({n_local * row_bytes / 1e6:.0f} MB) are L2-resident and the scan is bound by "
-                         "shared-memory LUT gathers (ncu: LSU pipe 87 %, issue 62 %, DRAM 1.5 %), not HBM; `traffic` = ncu DRAM bytes "
-                         "of one launch — see roofline_hbm_shape for the same kernel on a shard >> L2")}
+                "note": ("SURVEY 8d accounting: ceil(nq/T) passes over the packed rows (T queries share each pass; never multiplied "
+                         "back by T) + LUT/result bytes, divided by the scan kernel's CUDA-event time. "
+                         + (f"At this shape the packed codes of a GPU ({n_local * row_bytes / 1e6:.0f} MB) stay L2-resident while the query "
+                            "tiles sweep them, so HBM is not the limiter (`traffic` = ncu DRAM bytes of one launch): the kernel is bound "
+                            "by shared-memory table gathers (bound = smem_lsu); `peak` stays the HBM figure the accounting is defined "
+                            "against.  roofline_hbm_shape has the same kernel on a shard >> L2." if l2_resident else
+                            "The shard is far larger than L2: HBM-bound regime."))}
 
-    # ---- the same kernel on a shard far larger than L2 (the HBM-bound regime of the 100M / 1B-row shapes)
+    # ---- LUT build: bytes written / FMA utilisation (north_star: "for the LUT build it is tensor-pipe or FMA utilisation")
+    lut_ms_mean = float(np.mean(lut_ms))
+    nq_first = min(nq_rank, cfg["queries_per_launch"])
+    lut_written = nq_first * int(ix.lut_size) * (4 + (2 if cfg["scan_kernel"] == 3 else 0))
+    lut_flops = nq_first * int(ix.lut_size) * 3 * model.L
+    roofline_lut = {"bound": "hbm_write", "kernel": "lut_build_kernel", "launch_ms": lut_ms_mean, "bytes_written": lut_written,
+                    "achieved": lut_written / (lut_ms_mean / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": lut_written / (lut_ms_mean / 1e3) / 1e9 / peak,
+                    "flops": lut_flops, "fp32_tflops": lut_flops / (lut_ms_mean / 1e3) / 1e12,
+                    "fma_utilisation": lut_flops / (lut_ms_mean / 1e3) / 1e12 / FP32_FMA_PEAK_TFLOPS,
+                    "fp32_peak_tflops": FP32_FMA_PEAK_TFLOPS, "share_of_step": lut_ms_mean / (total_ms / args.steps),
+                    "note": "first batch of the step: scale + table kernels; nq * sum(K) * 3L flop (sub, mul, add), fp32 + fp16 tables written"}
+
+    # ---- the same scan kernel on a shard far larger than L2 (the HBM-bound regime of the 100M / 1B-row shapes)
     hbm_shape = None
     hamming = None
-    if not args.no_hbm_shape:
+    if not args.no_hbm_shape and world == 1:
         try:
             big_n = args.hbm_rows
             big = VAQIndex(model.L, model.bits, model.centroids, device=local_rank)
             big.reserve(big_n)
-            cdf = synth.code_cdf(ix.get_codes(0, min(n_local, 200_000)), model.bits)
+            cdf = pb.cdf if pb.cdf is not None else synth.code_cdf(ix.get_codes(0, min(n_local, 200_000)), model.bits)
             big.add_synthetic(big_n, SEED, cdf)
-            hbm_shape = {"rows": big_n, "packed_bytes": big_n * row_bytes, "peak": peak, "unit": "GB/s", "runs": []}
-            for bq in (4, 64):
+            hbm_shape = {"kernel": "adc_filter16_scan_kernel", "rows": big_n, "packed_bytes": big_n * row_bytes, "peak": peak, "unit": "GB/s",
+                         "bound": "hbm", "runs": []}
+            for bq in (1, 8, 64):
                 lab = torch.empty((bq, k), dtype=torch.int32, device=dev)
                 dis = torch.empty((bq, k), dtype=torch.float32, device=dev)
                 ms = []
@@ -413,19 +559,20 @@ def run_gpu_arm(args, w, name):
                 b = -(-bq // bT) * big_n * row_bytes + bq * lut_bytes
                 a = b / (np.mean(ms) / 1e3) / 1e9
                 hbm_shape["runs"].append({"queries": bq, "query_tile_T": bT, "scan_ms": float(np.mean(ms)), "achieved": a,
-                                          "frac": a / peak, "first_word_stream_GBps": -(-bq // bT) * big_n * 16 / (np.mean(ms) / 1e3) / 1e9,
+                                          "frac": a / peak, "traffic": ncu_traffic("adc_filter16_scan_kernel", f"hbm_shape_q{bq}", 1),
                                           "pairs_per_s": bq * big_n / (np.mean(ms) / 1e3), "config": bcfg})
+            best = max(hbm_shape["runs"][:2], key=lambda r: r["frac"])       # one query tile = one pass over HBM
+            hbm_shape.update({"achieved": best["achieved"], "frac": best["frac"], "traffic": best["traffic"]})
             big.close()
         except Exception as e:      # never hide the headline behind the auxiliary leg
             hbm_shape = {"error": repr(e)}
         try:
-            from vaq_b200.index import HammingIndex
             hn = args.hbm_rows
             hx = HammingIndex(256, device=local_rank)
             hx.add_synthetic(hn, SEED)
-            hamming = {"kernel": "ham_scan_kernel", "rows": hn, "bits": 256, "packed_bytes": hn * 32, "peak": peak, "unit": "GB/s",
-                       "runs": []}
-            for hq in (2, 64):
+            hamming = {"bound": "hbm", "kernel": "ham_scan_kernel", "rows": hn, "bits": 256, "packed_bytes": hn * 32, "peak": peak,
+                       "unit": "GB/s", "runs": []}
+            for hq in (1, 2, 8, 64):
                 hqv = torch.from_numpy(synth.synth_bitvectors(hq, 10 ** 10, 256, SEED).view(np.int64)).to(dev)
                 hidx = torch.empty((hq, k), dtype=torch.int32, device=dev)
                 hdist = torch.empty((hq, k), dtype=torch.int32, device=dev)
@@ -441,64 +588,89 @@ def run_gpu_arm(args, w, name):
                 b = -(-hq // qt) * hn * 32
                 a = b / (np.mean(ms) / 1e3) / 1e9
                 hamming["runs"].append({"queries": hq, "queries_per_pass": qt, "scan_ms": float(np.mean(ms)), "achieved": a,
-                                        "frac": a / peak, "qps": hq / (np.mean(ms) / 1e3),
-                                        "pairs_per_s": hq * hn / (np.mean(ms) / 1e3), "config": hcfg})
+                                        "frac": a / peak, "traffic": ncu_traffic("ham_scan_kernel", f"ham_q{hq}", 1),
+                                        "qps": hq / (np.mean(ms) / 1e3), "pairs_per_s": hq * hn / (np.mean(ms) / 1e3), "config": hcfg})
+            best = max(hamming["runs"], key=lambda r: r["frac"])
+            hamming.update({"achieved": best["achieved"], "frac": best["frac"], "traffic": best["traffic"],
+                            "best_at_queries": best["queries"]})
             hx.close()
         except Exception as e:
             hamming = {"error": repr(e)}
 
-    # ---- CPU baseline on the box's host cores + parity of the returned neighbours on the same queries
+    # ---- CPU baseline on the box's host cores + parity of the returned neighbours
     cpu = None
     parity = None
-    if not args.no_cpu and world > 1:
-        # multi-GPU: the merged answer of the first queries against the oracle's canonical answer on the whole matrix
+    if not args.no_cpu:
         from oracle import oracle as orc
+        threads = os.cpu_count() or 1
+        use_host_threads(threads)
         om = orc.Model(model.L, model.bits, model.centroids)
-        nchk = 32
-        try:        # torchrun exports OMP_NUM_THREADS=1; the checker may use the idle host cores
-            import ctypes
-            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(max(1, (os.cpu_count() or 1) // 2))
-        except OSError:
-            pass
-        codes_all = orc.Port().encode(om, XP)
-        wl, wd = orc.Port().search_lex(om, codes_all, Q[:nchk], k)
-        glab, gdis = lab_pin.numpy()[:nchk], dis_pin.numpy()[:nchk]
-        parity = {"queries": nchk, "checker": "oracle port, whole matrix", "ids_equal_frac": float((glab == wl).mean()),
-                  "dists_bit_equal": bool(np.array_equal(gdis.view(np.uint32), wd.view(np.uint32)))}
-    if not args.no_cpu and world == 1:
-        codes_local = ix.get_codes()
-        if world == 1:
-            threads = os.cpu_count() or 1
-            qps, n_used, kind, rlab, rdis, dt = cpu_reference_search(model, codes_local, Q, k, args.cpu_seconds, threads)
+        glab_all, gdis_all = lab_pin.numpy(), dis_pin.numpy()
+        if w["source"] == "vectors":
+            codes, rows_used, how = reference_codes(pb, args.cpu_rows)      # VAQ::encode of the compiled reference, all rows
+            parity = {}
+            if world == 1:
+                mine = ix.get_codes()
+                parity["device_encode_vs_reference_encode_mismatches"] = int((mine != codes).sum())
+                parity["codes_compared"] = int(codes.size)
+            qps, n_used, kind, rlab, rdis, dt = cpu_reference_search(model, codes, Q, k, args.cpu_seconds, threads)
             cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind,
                    "sample": f"{n_used} of {nq} queries, all {n} rows, EA mode, query-sliced over {threads} threads, {dt:.1f}s"}
-            glab = lab_pin.numpy()[:n_used]
-            gdis = dis_pin.numpy()[:n_used]
-            same = float((glab == rlab).mean())
-            rel = float(np.max(np.abs(gdis - rdis) / np.maximum(rdis, 1e-30)))
-            gt = synth.brute_force_knn(X, Qraw[:min(n_used, 200)], k)
-            parity = {"queries": n_used, "ids_equal_frac": same, "max_rel_dist_err": rel,
-                      "recall_at_10_gpu": synth.recall_at_k(glab[:gt.shape[0]], gt, k),
-                      "recall_at_10_reference": synth.recall_at_k(rlab[:gt.shape[0]], gt, k)}
+            glab, gdis = glab_all[:n_used], gdis_all[:n_used]
+            gt = synth.brute_force_knn(pb.X, pb.Qraw[:min(n_used, 200)], min(k, 10))
+            kk = min(k, 10)
+            parity.update({"checker": f"compiled {kind}: VAQ::search on the whole matrix", "queries": n_used,
+                           "ids_equal_frac": float((glab == rlab).mean()),
+                           "max_rel_dist_err": float(np.max(np.abs(gdis - rdis) / np.maximum(rdis, 1e-30))),
+                           "recall_at_10_gpu": synth.recall_at_k(glab[:gt.shape[0]], gt, kk),
+                           "recall_at_10_reference": synth.recall_at_k(rlab[:gt.shape[0]], gt, kk)})
+        else:
+            # the host cannot hold the matrix: CPU timing on a row slice (scaled), parity through size-independent checks
+            codes, rows_used, how = reference_codes(pb, args.cpu_rows)
+            qps, n_used, kind, rlab, rdis, dt = cpu_reference_search(model, codes, Q, k, args.cpu_seconds, threads)
+            cpu = {"value": qps * rows_used / n, "unit": "queries/s", "cores": threads, "kind": kind,
+                   "sample": f"{n_used} of {nq} queries, {how}, EA mode, query-sliced over {threads} threads, {dt:.1f}s"}
+            port = orc.Port()
+            nchk = min(nq, 16)
+            lut = port.create_lut(om, Q[:nchk])
+            ok_dist = ok_slice = ok_sorted = True
+            for q in range(nchk):
+                got = np.concatenate([pb.host_codes(int(r), 1) for r in glab_all[q]])
+                ok_dist &= bool(np.array_equal(port.adc_all(om, lut[q], got).view(np.uint32), gdis_all[q].view(np.uint32)))
+                d = port.adc_all(om, lut[q], codes)
+                better = np.nonzero(d < gdis_all[q, -1])[0]
+                ok_slice &= set(better.tolist()) <= set(glab_all[q].tolist())
+                ok_sorted &= bool((np.diff(gdis_all[q]) >= 0).all())
+            parity = {"checker": "oracle port on host-regenerated rows", "queries": nchk,
+                      "returned_distances_bit_equal_oracle": bool(ok_dist), "no_better_row_in_host_slice": bool(ok_slice),
+                      "sorted": bool(ok_sorted), "host_slice_rows": rows_used}
+            nl, nd = needle_out
+            lutn = port.create_lut(om, needle_q)
+            parity["planted_needles_ok"] = bool(all(
+                nd[j, 0] == port.adc_all(om, lutn[j], pb.host_codes(needles[j], 1))[0] and (nl[j, 0] == needles[j] or nd[j, 0] == nd[j, 1])
+                for j in range(len(needles))))
+            parity["planted_needles"] = len(needles)
 
     line = {
         "metric": "queries/sec at recall@10", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "rows": n, "dims": w["d"], "queries": nq, "k": k, "bits": w["budget"], "subspaces": w["M"],
-                   "mode": "EA", "row_bytes": row_bytes,
-                   "sharding": f"rows/{sh.R}" + (f" x queries/{sh.qgroups} (matrix replicated {sh.qgroups}x)" if sh.qgroups > 1 else ""), "l2": "256 MB fill between timed steps",
-                   "scan_config": cfg},
+        "config": dict(workload_config(name, w, "EA"), row_bytes=row_bytes,
+                       sharding=f"rows/{sh.R}" + (f" x queries/{sh.qgroups} (matrix replicated {sh.qgroups}x)" if sh.qgroups > 1 else ""),
+                       rows_per_gpu=n_local, bound_exchange="nvlink peer memory" if exchange else "off",
+                       l2="256 MB fill between timed steps", source=w["source"], desc=w["desc"], scan_config=cfg),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(Q.nbytes), "d2h_bytes_per_step": int(nq * k * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "row_sharded_layout": row_layout,
+        "roofline_lut_build": roofline_lut,
         "roofline_hbm_shape": hbm_shape,
-        "hamming_scan": hamming,
+        "roofline_hamming": hamming,
+        "hamming_sharded": hamming_sharded,
         "cpu_baseline": cpu,
         "parity_vs_cpu": parity,
-        "kernel_ms": {"lut_build": float(np.mean(lut_ms)), "adc_scan": scan_ms_mean, "merge": float(np.mean(merge_ms))},
+        "kernel_ms": {"lut_build": lut_ms_mean, "adc_scan": scan_ms_mean, "merge": float(np.mean(merge_ms)),
+                      "max_over_ranks": {"adc_scan": scan_max[0], "lut_build": scan_max[1], "merge": scan_max[2]}},
         "step_ms_rank0": [float(x) for x in step_ms],
     }
     emit(line)
@@ -514,18 +686,26 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sift1m_256b_m32_k10", choices=sorted(WORKLOADS))
+    ap.add_argument("--queries", type=int, default=0, help="override the workload's query count")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="host row slice for the CPU baseline of device-generated workloads")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hbm-shape", action="store_true")
+    ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-bound-exchange", action="store_true", help="comparison: shards prune with their own bounds only")
     ap.add_argument("--hbm-rows", type=int, default=64_000_000)
+    ap.add_argument("--ham-rows", type=int, default=256_000_000, help="total rows of the row-sharded Hamming leg")
+    ap.add_argument("--ham-queries", type=int, default=64)
     ap.add_argument("--scan-v1", action="store_true", help="force the lane-per-row scan kernel (comparison)")
     ap.add_argument("--row-shards", type=int, default=0,
-                    help="R: ranks per replica group (default N = pure row sharding, the BASELINE layout); R < N replicates the "
-                         "code matrix N/R times and splits the query batch between the groups")
+                    help="experiment knob; default 0 = N row shards (pure row sharding, the BASELINE layout).  R < N replicates "
+                         "the code matrix N/R times and splits the query batch between the replica groups")
     args = ap.parse_args()
     capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.queries:
+        w["nq"] = args.queries
     if args.impl == "reference":
         run_reference_arm(args, w, args.workload)
     else:

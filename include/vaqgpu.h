@@ -120,6 +120,20 @@ int vaqgpu_search_keys_device(vaqgpu_t *h, const float *d_queries, int32_t nq, i
 int vaqgpu_merge_keys_device(const uint64_t *d_keys_in, int32_t G, int32_t nq, int32_t k, uint32_t flags,
                              int32_t *d_labels, float *d_dists, void *stream);
 
+/* ---- cross-shard bound exchange (row-sharded deployments) ------------------------
+ * Each shard owns a per-query array of "best k-th distance proven so far"; its scan publishes every new bound into
+ * its own array and — through NVLink peer memory — into the arrays of the other shards, so all GPUs prune with the
+ * tightest bound found anywhere (the reference's single running bsfK, VAQ.cpp:1700-1721, spans all rows; without
+ * the exchange a shard only knows the k-th best of its own N/G rows).  Results are unchanged (exact pruning).
+ *  - vaqgpu_bounds_export allocates the array (searches with nq <= max_queries use it), returns its device pointer
+ *    and a 64-byte CUDA IPC handle for shards living in other processes (either out-pointer may be NULL);
+ *  - vaqgpu_bounds_attach_ipc / _ptr hand this shard the arrays of its n_peers (<= 15) peers;
+ *  - from then on vaqgpu_search*_device must be called collectively: every shard runs the same sequence of searches
+ *    (same queries), each followed by a collective that waits for all shards (the all-gather of the key lists). */
+int vaqgpu_bounds_export(vaqgpu_t *h, int32_t max_queries, unsigned char ipc_handle[64], void **d_ptr);
+int vaqgpu_bounds_attach_ipc(vaqgpu_t *h, int32_t n_peers, const unsigned char *ipc_handles /* n_peers x 64 */);
+int vaqgpu_bounds_attach_ptr(vaqgpu_t *h, int32_t n_peers, void *const *peer_ptrs);
+
 /* TI / visit mode (replaces VAQ::clusterTI's outputs + searchTriangleInequality, VAQ.cpp:878-999,
  * 1540-1692).  The index rows must already be in cluster-grouped order (as clusterTI leaves
  * mCodebook).  clusters: [C x segdims]; start/size: [C] row ranges; id_map: [n] original id of each
@@ -170,6 +184,33 @@ int hamgpu_merge_keys_device(const uint64_t *d_keys_in, int32_t G, int32_t nq, i
                              int32_t *d_idx, uint32_t *d_dist, void *stream);
 int hamgpu_last_timings(const hamgpu_t *h, float ms[2]); /* [0]=scan, [1]=merge/output */
 int hamgpu_last_config(const hamgpu_t *h, int32_t cfg[8]);
+
+/* ---- row-sharded handles: one host process, n_gpus devices -------------------
+ * Shard r holds global rows [r * ceil(N/G), (r+1) * ceil(N/G)) of an index of n_rows_total rows; rows are appended in
+ * global order and split at the shard boundaries.  A search copies the query batch to every GPU, runs the shard-local
+ * scans concurrently (one stream per device; running k-th-best bounds exchanged through NVLink peer memory), gathers
+ * the shard-local top-k key lists with one ncclAllGather (ncclCommInitAll communicator; NCCL is loaded at run time)
+ * and merges them on the first device: same answer as one unsharded index, bit for bit.  dev_ids == NULL: 0..n_gpus-1.
+ * The merge rule's precedent in the reference: BitVecEngine.cpp:1599-1611. */
+typedef struct vaqgpu_sharded vaqgpu_sharded_t;
+typedef struct hamgpu_sharded hamgpu_sharded_t;
+int vaqgpu_sharded_create(const vaqgpu_model_desc *model, int32_t n_gpus, const int *dev_ids, int64_t n_rows_total,
+                          vaqgpu_sharded_t **out);
+void vaqgpu_sharded_destroy(vaqgpu_sharded_t *h);
+int vaqgpu_sharded_add_codes_u16(vaqgpu_sharded_t *h, const uint16_t *codes, int64_t n);
+int vaqgpu_sharded_encode_add(vaqgpu_sharded_t *h, const float *x_proj, int64_t n);
+int vaqgpu_sharded_add_codes_synthetic(vaqgpu_sharded_t *h, int64_t n, uint64_t seed, const float *cdf);
+int vaqgpu_sharded_num_shards(const vaqgpu_sharded_t *h, int32_t *n);
+int vaqgpu_sharded_shard(vaqgpu_sharded_t *h, int32_t r, vaqgpu_t **shard);   /* borrowed: per-shard introspection */
+/* replaces VAQ::search on the sharded index; host buffers, EA / HEAP flags (see vaqgpu_search) */
+int vaqgpu_sharded_search(vaqgpu_sharded_t *h, const float *queries, int32_t nq, int32_t k, uint32_t flags,
+                          int32_t *labels, float *dists);
+int hamgpu_sharded_create(int32_t nbits, int32_t n_gpus, const int *dev_ids, int64_t n_rows_total, hamgpu_sharded_t **out);
+void hamgpu_sharded_destroy(hamgpu_sharded_t *h);
+int hamgpu_sharded_add(hamgpu_sharded_t *h, const uint64_t *words, int64_t n);
+int hamgpu_sharded_add_synthetic(hamgpu_sharded_t *h, int64_t n, uint64_t seed);
+/* replaces BitVecEngine::query / queryParallel on the sharded bit-vector matrix */
+int hamgpu_sharded_query(hamgpu_sharded_t *h, const uint64_t *queries, int32_t nq, int32_t k, int32_t *idx, uint32_t *dist);
 
 #ifdef __cplusplus
 }

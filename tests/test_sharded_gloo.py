@@ -55,6 +55,22 @@ def _worker(rank, world, port, out):
     hi_, hd_ = split_keys(mh, hamming=True)
     wi, wd = hamming_lex(data, q, 5)
     ok = ok and bool(np.array_equal(hi_, wi) and np.array_equal(hd_, wd))
+    # bound exchange plumbing: every shard receives the IPC handles of the OTHER shards of its group, in shard order
+    from vaq_b200.sharded import ShardedVAQ
+
+    class StubIndex:
+        device = 0
+
+        def bounds_export(self, max_queries):
+            return bytes([rank + 1]) * 64, 0
+
+        def bounds_attach_ipc(self, handles):
+            self.got = handles
+
+    shv = object.__new__(ShardedVAQ)
+    shv.rank, shv.world, shv.group, shv.R, shv.qgroups, shv.r, shv.qg = rank, world, None, world, 1, rank, 0
+    shv.index = StubIndex()
+    ok = ok and shv.enable_bound_exchange(100) and shv.index.got == [bytes([r + 1]) * 64 for r in range(world) if r != rank]
     out[rank] = ok
     dist.barrier()
     dist.destroy_process_group()

@@ -50,6 +50,9 @@ PROTOTYPES = {
     "vaqgpu_search_device": (C.c_int, [_p, _p, _i32, _i32, _u32, _p, _p, _p]),
     "vaqgpu_search_keys_device": (C.c_int, [_p, _p, _i32, _i32, _u32, _p, _p]),
     "vaqgpu_merge_keys_device": (C.c_int, [_p, _i32, _i32, _i32, _u32, _p, _p, _p]),
+    "vaqgpu_bounds_export": (C.c_int, [_p, _i32, _p, C.POINTER(_p)]),
+    "vaqgpu_bounds_attach_ipc": (C.c_int, [_p, _i32, _p]),
+    "vaqgpu_bounds_attach_ptr": (C.c_int, [_p, _i32, C.POINTER(_p)]),
     "vaqgpu_set_clusters": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p]),
     "vaqgpu_set_visit": (C.c_int, [_p, _f]),
     "vaqgpu_set_raw_vectors": (C.c_int, [_p, _p, _i64, _i32]),
@@ -68,6 +71,19 @@ PROTOTYPES = {
     "hamgpu_merge_keys_device": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p]),
     "hamgpu_last_timings": (C.c_int, [_p, C.POINTER(_f)]),
     "hamgpu_last_config": (C.c_int, [_p, C.POINTER(_i32)]),
+    "vaqgpu_sharded_create": (C.c_int, [C.POINTER(ModelDesc), _i32, C.POINTER(C.c_int), _i64, C.POINTER(_p)]),
+    "vaqgpu_sharded_destroy": (None, [_p]),
+    "vaqgpu_sharded_add_codes_u16": (C.c_int, [_p, _p, _i64]),
+    "vaqgpu_sharded_encode_add": (C.c_int, [_p, _p, _i64]),
+    "vaqgpu_sharded_add_codes_synthetic": (C.c_int, [_p, _i64, _u64, _p]),
+    "vaqgpu_sharded_num_shards": (C.c_int, [_p, C.POINTER(_i32)]),
+    "vaqgpu_sharded_shard": (C.c_int, [_p, _i32, C.POINTER(_p)]),
+    "vaqgpu_sharded_search": (C.c_int, [_p, _p, _i32, _i32, _u32, _p, _p]),
+    "hamgpu_sharded_create": (C.c_int, [_i32, _i32, C.POINTER(C.c_int), _i64, C.POINTER(_p)]),
+    "hamgpu_sharded_destroy": (None, [_p]),
+    "hamgpu_sharded_add": (C.c_int, [_p, _p, _i64]),
+    "hamgpu_sharded_add_synthetic": (C.c_int, [_p, _i64, _u64]),
+    "hamgpu_sharded_query": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
 }
 
 _lib = None

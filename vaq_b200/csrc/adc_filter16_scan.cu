@@ -262,7 +262,10 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
       if (lane == 0 && lo < 0x7C00u) {
         const float x = __half2float(__ushort_as_half((unsigned short)lo));
         const float ub = (x * (1.f + 1.f / 16.f) + (float)M * 5.9604645e-8f) / scale_s[warp] * (1.f + 1e-6f) + 1e-30f;
-        if (ub < 3.0e38f) publish_bound(warp, __float_as_uint(ub));
+        if (ub < 3.0e38f) {
+          publish_bound(warp, __float_as_uint(ub));
+          publish_global_bound(a.thr_global, a.peers, q0 + warp, __float_as_uint(ub));      // a valid bound for every chunk and shard
+        }
       }
     }
     __syncthreads();
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
               if (kth != before && kth != kEmptyKey) {
                 const uint32_t bits = (uint32_t)(kth >> 32);
                 publish_bound(tt, bits);
-                atomicMin(a.thr_global + q0 + tt, bits);
+                publish_global_bound(a.thr_global, a.peers, q0 + tt, bits);
               }
             }
           }

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
               if (kth != before && kth != kEmptyKey) {
                 const uint32_t bits = (uint32_t)(kth >> 32);
                 atomicMin(thr_f + tt, bits);
-                if (q0 + tt < a.nq) atomicMin(a.thr_global + q0 + tt, bits);
+                if (q0 + tt < a.nq) publish_global_bound(a.thr_global, a.peers, q0 + tt, bits);
               }
             }
           }

@@ -173,6 +173,26 @@ __device__ __forceinline__ void block_merge_lists(const uint64_t *lists, int nli
 
 #endif  // __CUDACC__
 
+// ---- cross-shard bound exchange ----------------------------------------------------------
+// Row-sharded search: every shard owns a per-query array of the best k-th distance proven so far (float bits,
+// 0xFFFFFFFF = none).  A scan publishes each new bound into its own array AND, through NVLink peer memory, into the
+// arrays of the other shards, so every GPU prunes with the tightest bound found anywhere on the box.  Exact: a
+// shard's k-th best distance is an upper bound of the k-th best over all shards, and a row of the global top-k is in
+// its own shard's top-k with a distance <= that bound, so no shard ever drops it.
+constexpr int kMaxPeers = 15;
+struct PeerBounds {
+  uint32_t *p[kMaxPeers];    // the same array on the other shards (peer-mapped device pointers)
+  int32_t n;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void publish_global_bound(uint32_t *own, const PeerBounds &peers, int q, uint32_t bits) {
+  if (atomicMin(own + q, bits) > bits) {            // only a bound that is new here travels
+    for (int i = 0; i < peers.n; i++) atomicMin(peers.p[i] + q, bits);      // fire-and-forget RED.MIN over NVLink
+  }
+}
+#endif
+
 // ---- launchers (one per .cu) ----------------------------------------------------------
 struct AdcScanArgs {
   const uint4 *codes;        // packed tiles [tile][w][lane]
@@ -208,6 +228,7 @@ struct AdcFilterArgs {
   int32_t slot_base;         // this launch's first list
   uint64_t *out_keys;        // [nq][out_slots][k]; low word = LOCAL row index
   uint32_t *thr_global;      // [nq] float bits of the best known k-th distance (0xFFFFFFFF = none)
+  PeerBounds peers;          // the same array on the other row shards (n = 0: single shard)
   int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
   ScanLayout lay;
 };
@@ -228,6 +249,7 @@ struct AdcFilter16Args {
   int32_t chunk_tiles, out_slots, slot_base;
   uint64_t *out_keys;
   uint32_t *thr_global;
+  PeerBounds peers;          // the same array on the other row shards (n = 0: single shard)
   int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
   long long *dbg;            // development: per-CTA phase clocks (NULL = off)
   ScanLayout lay;

@@ -59,48 +59,47 @@ __device__ __forceinline__ float l2sqr_small(const float *__restrict__ x, const 
 // One thread per table entry and query TILE: the centroid is read once, the T queries of the tile are
 // scored against it and the T values are written as one contiguous T*4-byte store — the interleaved
 // [entry][T] layout the scan kernels read — so the stores of a warp are fully coalesced.  Optionally the
-// same thread also writes the fp16 lower-bound entries for the tile (T == 8 only):
+// same thread also writes the fp16 lower-bound entries for the tile (T == 8 only; scales from lut_scale_kernel):
 //     e16 = round_toward_zero(scale_t * value),   scale_t = 2^floor(log2(16000 / ub_t)),
 //     ub_t = max_s (|q_t,s| + max_c |C_s[c]|)^2  >= every entry of query t (triangle inequality),
 // so scale_t * entry <= 16000 and four entries still sum below the fp16 maximum.  fp16 keeps 11 significant
 // bits at any scale, so the looseness of ub only costs exponent range.
+// Per-query scale of the fp16 lower-bound tables, one warp per query (run once per batch, before lut_build_kernel<8>).
+__global__ void __launch_bounds__(256) lut_scale_kernel(const float *__restrict__ q_proj, int nq, int nq_pad, int D, int M, int L,
+                                                        const float *__restrict__ cent_rmax, float *__restrict__ scale) {
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), ln = threadIdx.x & 31;
+  if (qi >= nq_pad) return;
+  const int q = min(qi, nq - 1);               // slots past nq (tile padding) repeat the last query
+  float ub = 0.f;
+  for (int s = ln; s < M; s += 32) {
+    const float *qs = q_proj + (size_t)q * D + (size_t)s * L;
+    float n2 = 0.f;
+    for (int j = 0; j < L; j++) n2 = fmaf(qs[j], qs[j], n2);
+    const float r = sqrtf(n2) + cent_rmax[s];
+    ub = fmaxf(ub, r * r);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ub = fmaxf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+  if (ln == 0) {
+    float sc = 1.f;
+    ub *= 1.0001f;                       // the entries are computed with rounding; keep a hair of slack
+    if (ub > 0.f && ub < 3.0e38f) {
+      int ex = (int)floorf(log2f(16000.f / ub));
+      ex = max(-100, min(100, ex));
+      sc = exp2f((float)ex);
+      while (ub * sc > 16000.f) sc *= 0.5f;
+    }
+    scale[qi] = sc;
+  }
+}
+
 template <int T>
 __global__ void __launch_bounds__(256) lut_build_kernel(const float *__restrict__ q_proj, int nq, int D, const float *__restrict__ cent,
-                                                        const float *__restrict__ cent_rmax, const __grid_constant__ LutPlan p,
+                                                        const __grid_constant__ LutPlan p,
                                                         float *__restrict__ lut, __half *__restrict__ lut16,
-                                                        float *__restrict__ scale) {
-  __shared__ float sscale[T];
+                                                        const float *__restrict__ scale) {
   const int qt = blockIdx.y;
   const int L = p.L;
-  if (lut16 != nullptr) {
-    const int t = threadIdx.x >> 5, ln = threadIdx.x & 31;       // one warp per query of the tile
-    if (t < T) {
-      const int q = min(qt * T + t, nq - 1);
-      float ub = 0.f;
-      for (int s = ln; s < p.M; s += 32) {
-        const float *qs = q_proj + (size_t)q * D + (size_t)s * L;
-        float n2 = 0.f;
-        for (int j = 0; j < L; j++) n2 = fmaf(qs[j], qs[j], n2);
-        const float r = sqrtf(n2) + cent_rmax[s];
-        ub = fmaxf(ub, r * r);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ub = fmaxf(ub, __shfl_xor_sync(0xffffffffu, ub, o));
-      if (ln == 0) {
-        float sc = 1.f;
-        ub *= 1.0001f;                       // the entries are computed with rounding; keep a hair of slack
-        if (ub > 0.f && ub < 3.0e38f) {
-          int ex = (int)floorf(log2f(16000.f / ub));
-          ex = max(-100, min(100, ex));
-          sc = exp2f((float)ex);
-          while (ub * sc > 16000.f) sc *= 0.5f;
-        }
-        sscale[t] = sc;
-        if (blockIdx.x == 0) scale[qt * T + t] = sc;
-      }
-    }
-    __syncthreads();
-  }
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.total_entries) return;
   int lo = 0, hi = p.M;
@@ -140,10 +139,13 @@ __global__ void __launch_bounds__(256) lut_build_kernel(const float *__restrict_
   }
   if constexpr (T == 8) {
     if (lut16 != nullptr) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4 *>(scale + (size_t)qt * T));
+      const float4 s1 = __ldg(reinterpret_cast<const float4 *>(scale + (size_t)qt * T + 4));
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
       __half2 h[4];
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        h[i] = __halves2half2(__float2half_rz(acc[2 * i] * sscale[2 * i]), __float2half_rz(acc[2 * i + 1] * sscale[2 * i + 1]));
+        h[i] = __halves2half2(__float2half_rz(acc[2 * i] * sc[2 * i]), __float2half_rz(acc[2 * i + 1] * sc[2 * i + 1]));
       *reinterpret_cast<uint4 *>(lut16 + o) = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
                                                         *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
     }
@@ -158,11 +160,15 @@ cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, 
   const int T = plan.T;
   dim3 grid((unsigned)((plan.total_entries + threads - 1) / threads), (unsigned)((nq_launch + T - 1) / T));
   __half *l16 = reinterpret_cast<__half *>(lut16);
+  if (T == 8 && l16 != nullptr) {
+    const int nq_pad = (nq_launch + T - 1) / T * T;
+    lut_scale_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q_proj, nq, nq_pad, D, plan.M, plan.L, cent_rmax, scale);
+  }
   switch (T) {
-    case 1: lut_build_kernel<1><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, cent_rmax, plan, lut, nullptr, nullptr); break;
-    case 2: lut_build_kernel<2><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, cent_rmax, plan, lut, nullptr, nullptr); break;
-    case 4: lut_build_kernel<4><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, cent_rmax, plan, lut, nullptr, nullptr); break;
-    case 8: lut_build_kernel<8><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, cent_rmax, plan, lut, l16, scale); break;
+    case 1: lut_build_kernel<1><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
+    case 2: lut_build_kernel<2><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
+    case 4: lut_build_kernel<4><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
+    case 8: lut_build_kernel<8><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, l16, scale); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

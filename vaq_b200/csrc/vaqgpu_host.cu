@@ -30,6 +30,21 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+namespace vaqgpu {
+// same message slot, for the other translation units of the library (sharded.cu)
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace vaqgpu
+
+namespace {
+
 #define CU(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -113,6 +128,13 @@ struct vaqgpu_index {
   cudaEvent_t ev[5] = {};
   bool timed = false;
   int32_t cfg[12] = {};
+
+  // cross-shard bound exchange (vaqgpu_bounds_*): two halves of bounds_cap entries, used alternately by
+  // successive searches; the half the NEXT search will use is reset while this one runs
+  uint32_t *d_bounds = nullptr;
+  int32_t bounds_cap = 0, bounds_parity = 0;
+  PeerBounds peers{};
+  std::vector<void *> ipc_opened;
 
   DevBuf w_dbg, w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
 };
@@ -341,6 +363,28 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   LutPlan plan;
   int32_t res_floats = 0, spill_floats = 0;
 
+  // Per-query bound array of this search (filter kernels).  With an exported array (row-sharded deployment) the
+  // search uses one half and resets the other for the next search: peers only write a half between this shard's
+  // reset of it and the end of the search that uses it, because every search ends in a collective (the all-gather
+  // of the key lists) that no shard passes before all shards finished scanning.
+  uint32_t *thr_all = nullptr;
+  PeerBounds peers{};
+  if (filter) {
+    if (h->d_bounds && nq <= h->bounds_cap) {
+      thr_all = h->d_bounds + (size_t)h->bounds_parity * h->bounds_cap;
+      uint32_t *next = h->d_bounds + (size_t)(h->bounds_parity ^ 1) * h->bounds_cap;
+      for (int i = 0; i < h->peers.n; i++) peers.p[i] = h->peers.p[i] + (size_t)h->bounds_parity * h->bounds_cap;
+      peers.n = h->peers.n;
+      CU(launch_fill_u32(next, h->bounds_cap, 0xFFFFFFFFu, st));
+      h->bounds_parity ^= 1;
+    } else {
+      CU(h->w_thr.ensure((size_t)nq * sizeof(uint32_t)));
+      thr_all = (uint32_t *)h->w_thr.p;
+      CU(launch_fill_u32(thr_all, nq, 0xFFFFFFFFu, st));
+    }
+    launches++;
+  }
+
   // ---- fp16 lower-bound tables, query tiles of 8 (default when eight queries' tables fit) -------------
   bool filter16 = filter && !(flags & VAQGPU_SCAN_F32) && nq >= tune_knob("min16", 1);
   if (filter16) {
@@ -367,7 +411,6 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     CU(h->w_lut16.ensure((size_t)qb_max * bytes_per_q / 2));
     CU(h->w_scale.ensure((size_t)qb_max * sizeof(float)));
     CU(h->w_keys.ensure((size_t)qb_max * out_slots * k * sizeof(uint64_t)));
-    CU(h->w_thr.ensure((size_t)qb_max * sizeof(uint32_t)));
     if (out_slots > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((out_slots + 15) / 16) * k * sizeof(uint64_t)));
 
     for (int q0 = 0; q0 < nq; q0 += qb_max) {
@@ -376,7 +419,6 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       const float *qp = d_qproj + (size_t)q0 * h->D;
       CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, h->d_cent_rmax, plan, (float *)h->w_lut.p, h->w_lut16.p,
                           (float *)h->w_scale.p, st));
-      CU(launch_fill_u32((uint32_t *)h->w_thr.p, qb, 0xFFFFFFFFu, st));
       launches += 2;
       if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
       AdcFilter16Args a{};
@@ -386,7 +428,9 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.nq = qb; a.k = k; a.out_slots = out_slots; a.slot_base = 0;
       a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles;
       a.out_keys = (uint64_t *)h->w_keys.p;
-      a.thr_global = (uint32_t *)h->w_thr.p;
+      a.thr_global = thr_all + q0;
+      a.peers = peers;
+      for (int i = 0; i < peers.n; i++) a.peers.p[i] += q0;
       a.seed = tune_knob("seed", 1);
       a.lay = lay;
       const bool dbg = tune_knob("dbg", 0) != 0;
@@ -452,7 +496,6 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
 
     CU(h->w_lut.ensure((size_t)qb_max * bytes_per_q));
     CU(h->w_keys.ensure((size_t)qb_max * out_slots * k * sizeof(uint64_t)));
-    CU(h->w_thr.ensure((size_t)qb_max * sizeof(uint32_t)));
     if (out_slots > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((out_slots + 15) / 16) * k * sizeof(uint64_t)));
 
     for (int q0 = 0; q0 < nq; q0 += qb_max) {
@@ -460,15 +503,16 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       const int qb_pad = (qb + T - 1) / T * T;
       const float *qp = d_qproj + (size_t)q0 * h->D;
       CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, h->d_cent_rmax, plan, (float *)h->w_lut.p, nullptr, nullptr, st));
-      CU(launch_fill_u32((uint32_t *)h->w_thr.p, qb, 0xFFFFFFFFu, st));
-      launches += 2;
+      launches += 1;
       if (record && q0 == 0) CU(cudaEventRecord(h->ev[2], st));
       AdcFilterArgs a{};
       a.codes = h->d_codes; a.n_rows = h->n_rows;
       a.lut = (const float *)h->w_lut.p; a.lut_stride = plan.row_stride; a.smem_lut_floats = res_floats;
       a.nq = qb; a.k = k; a.out_slots = out_slots;
       a.out_keys = (uint64_t *)h->w_keys.p;
-      a.thr_global = (uint32_t *)h->w_thr.p;
+      a.thr_global = thr_all + q0;
+      a.peers = peers;
+      for (int i = 0; i < peers.n; i++) a.peers.p[i] += q0;
       a.lay = lay;
       a.seed = tune_knob("seed", 1);
       a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles; a.slot_base = 0;
@@ -642,6 +686,8 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   cudaFree(h->d_centroids); cudaFree(h->d_cent_rmax); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
   cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size);
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(h->d_bounds);
   for (DevBuf *b : {&h->w_dbg, &h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
                     &h->w_labels, &h->w_dists, &h->w_outkeys, &h->w_cdf, &h->w_x})
     b->release();
@@ -895,6 +941,60 @@ int vaqgpu_refine(vaqgpu_t *h, const float *queries, int32_t nq, const int32_t *
   CU(cudaMemcpyAsync(labels, h->w_labels.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(dists, h->w_dists.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return VAQGPU_OK;
+}
+
+/* ---- cross-shard bound exchange -------------------------------------------------------------- */
+
+int vaqgpu_bounds_export(vaqgpu_t *h, int32_t max_queries, unsigned char ipc_handle[64], void **d_ptr) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  if (max_queries < 1) return fail(VAQGPU_EINVAL, "max_queries=%d", max_queries);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceGuard g(h->device);
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  h->ipc_opened.clear();
+  h->peers.n = 0;
+  cudaFree(h->d_bounds);
+  h->d_bounds = nullptr; h->bounds_cap = 0; h->bounds_parity = 0;
+  const int32_t cap = (max_queries + 63) & ~63;
+  CU(cudaMalloc(&h->d_bounds, (size_t)2 * cap * sizeof(uint32_t)));
+  CU(cudaMemset(h->d_bounds, 0xFF, (size_t)2 * cap * sizeof(uint32_t)));
+  CU(cudaDeviceSynchronize());
+  h->bounds_cap = cap;
+  if (ipc_handle) {
+    cudaIpcMemHandle_t ih;
+    CU(cudaIpcGetMemHandle(&ih, h->d_bounds));
+    memcpy(ipc_handle, &ih, 64);
+  }
+  if (d_ptr) *d_ptr = h->d_bounds;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_bounds_attach_ipc(vaqgpu_t *h, int32_t n_peers, const unsigned char *ipc_handles) {
+  if (!h || (n_peers > 0 && !ipc_handles)) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (!h->d_bounds) return fail(VAQGPU_ESTATE, "vaqgpu_bounds_export first");
+  if (n_peers < 0 || n_peers > kMaxPeers) return fail(VAQGPU_EINVAL, "n_peers=%d (0..%d)", n_peers, kMaxPeers);
+  DeviceGuard g(h->device);
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  h->ipc_opened.clear();
+  h->peers.n = 0;
+  for (int i = 0; i < n_peers; i++) {
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, ipc_handles + (size_t)i * 64, 64);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    h->peers.p[h->peers.n++] = (uint32_t *)p;
+  }
+  return VAQGPU_OK;
+}
+
+int vaqgpu_bounds_attach_ptr(vaqgpu_t *h, int32_t n_peers, void *const *peer_ptrs) {
+  if (!h || (n_peers > 0 && !peer_ptrs)) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (!h->d_bounds) return fail(VAQGPU_ESTATE, "vaqgpu_bounds_export first");
+  if (n_peers < 0 || n_peers > kMaxPeers) return fail(VAQGPU_EINVAL, "n_peers=%d (0..%d)", n_peers, kMaxPeers);
+  h->peers.n = 0;
+  for (int i = 0; i < n_peers; i++) h->peers.p[h->peers.n++] = (uint32_t *)peer_ptrs[i];
   return VAQGPU_OK;
 }
 

@@ -143,6 +143,23 @@ class VAQIndex:
         check(self.lib.vaqgpu_merge_keys_device(C.c_void_p(d_keys_in), G, nq, k, flags, C.c_void_p(d_labels),
                                                 C.c_void_p(d_dists), C.c_void_p(stream)))
 
+    # -- cross-shard bound exchange (row-sharded deployments)
+    def bounds_export(self, max_queries: int) -> tuple[bytes, int]:
+        """Allocates this shard's bound array; returns (64-byte CUDA IPC handle, device pointer)."""
+        buf = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        check(self.lib.vaqgpu_bounds_export(self.h, int(max_queries), buf, C.byref(ptr)))
+        return bytes(buf), int(ptr.value)
+
+    def bounds_attach_ipc(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        arr = (C.c_ubyte * max(1, len(blob))).from_buffer_copy(blob or b"\0")
+        check(self.lib.vaqgpu_bounds_attach_ipc(self.h, len(handles), arr))
+
+    def bounds_attach_ptr(self, ptrs: list[int]):
+        arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
+        check(self.lib.vaqgpu_bounds_attach_ptr(self.h, len(ptrs), arr))
+
     # -- TI / visit, refine
     def set_clusters(self, clusters, start, size, id_map=None):
         cl = _c(clusters, np.float32)
@@ -252,3 +269,93 @@ class HammingIndex:
         check(self.lib.hamgpu_last_config(self.h, cfg))
         keys = ["threads", "splits", "queries_per_cta", "_", "smem_bytes", "row_words", "launches", "queries_per_launch"]
         return dict(zip(keys, list(cfg)))
+
+
+class VAQShardedIndex:
+    """One host process, ``n_gpus`` devices: the row-sharded index behind ``vaqgpu_sharded_*`` (contiguous row blocks,
+    peer-memory bound exchange, one ncclAllGather of the shard-local key lists, device merge)."""
+
+    def __init__(self, L: int, bits, centroids, n_rows_total: int, eig=None, n_gpus: int = 1, dev_ids=None):
+        self.lib = _lib.load()
+        self.bits = _c(bits, np.int32)
+        self.M, self.L = int(self.bits.size), int(L)
+        self.D = self.M * self.L
+        flat = np.concatenate([_c(c, np.float32).reshape(-1) for c in centroids]).astype(np.float32)
+        eig_arr = None if eig is None else _c(eig, np.float32)
+        desc = ModelDesc(self.D, self.M, self.L, self.bits.ctypes.data_as(C.POINTER(C.c_int32)),
+                         flat.ctypes.data_as(C.POINTER(C.c_float)),
+                         None if eig_arr is None else eig_arr.ctypes.data_as(C.POINTER(C.c_float)))
+        ids = None if dev_ids is None else (C.c_int * n_gpus)(*[int(d) for d in dev_ids])
+        h = C.c_void_p()
+        check(self.lib.vaqgpu_sharded_create(C.byref(desc), int(n_gpus), ids, int(n_rows_total), C.byref(h)))
+        self.h, self.n_gpus = h, int(n_gpus)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vaqgpu_sharded_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_codes(self, codes):
+        codes = _c(codes, np.uint16)
+        check(self.lib.vaqgpu_sharded_add_codes_u16(self.h, _vp(codes), codes.shape[0]))
+
+    def encode_add(self, x_proj):
+        x = _c(x_proj, np.float32)
+        check(self.lib.vaqgpu_sharded_encode_add(self.h, _vp(x), x.shape[0]))
+
+    def add_synthetic(self, n: int, seed: int, cdf=None):
+        cdf_arr = None if cdf is None else _c(cdf, np.float32)
+        check(self.lib.vaqgpu_sharded_add_codes_synthetic(self.h, int(n), C.c_uint64(seed), None if cdf_arr is None else _vp(cdf_arr)))
+
+    def search(self, queries, k: int, flags: int = EA | PROJECTED):
+        q = _c(queries, np.float32).reshape(-1, self.D)
+        labels = np.empty((q.shape[0], k), np.int32)
+        dists = np.empty((q.shape[0], k), np.float32)
+        check(self.lib.vaqgpu_sharded_search(self.h, _vp(q), q.shape[0], int(k), int(flags), _vp(labels), _vp(dists)))
+        return labels, dists
+
+    def search_into(self, q: np.ndarray, k: int, flags: int, labels: np.ndarray, dists: np.ndarray):
+        check(self.lib.vaqgpu_sharded_search(self.h, _vp(q), q.shape[0], int(k), int(flags), _vp(labels), _vp(dists)))
+
+
+class HammingShardedIndex:
+    """One host process, ``n_gpus`` devices: ``hamgpu_sharded_*``."""
+
+    def __init__(self, nbits: int, n_rows_total: int, n_gpus: int = 1, dev_ids=None):
+        self.lib = _lib.load()
+        self.nbits, self.w64 = int(nbits), (int(nbits) + 63) // 64
+        ids = None if dev_ids is None else (C.c_int * n_gpus)(*[int(d) for d in dev_ids])
+        h = C.c_void_p()
+        check(self.lib.hamgpu_sharded_create(self.nbits, int(n_gpus), ids, int(n_rows_total), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hamgpu_sharded_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, words):
+        w = _c(words, np.uint64).reshape(-1, self.w64)
+        check(self.lib.hamgpu_sharded_add(self.h, _vp(w), w.shape[0]))
+
+    def add_synthetic(self, n: int, seed: int):
+        check(self.lib.hamgpu_sharded_add_synthetic(self.h, int(n), C.c_uint64(seed)))
+
+    def query(self, queries, k: int):
+        q = _c(queries, np.uint64).reshape(-1, self.w64)
+        idx = np.empty((q.shape[0], k), np.int32)
+        dist = np.empty((q.shape[0], k), np.uint32)
+        check(self.lib.hamgpu_sharded_query(self.h, _vp(q), q.shape[0], int(k), _vp(idx), _vp(dist)))
+        return idx, dist

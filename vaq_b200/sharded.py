@@ -76,6 +76,35 @@ class ShardedVAQ:
         self.index.set_id_base(self.lo)
         self.index.reserve(max(1, self.hi - self.lo))
 
+    def enable_bound_exchange(self, max_queries: int, exchange=None) -> bool:
+        """Lets the shards of this rank's replica group publish their running k-th-best bounds into each other's HBM
+        over NVLink (vaqgpu_bounds_*; CUDA IPC handles travel through one all-gather).  Collective over the world.
+        Returns False (and changes nothing) when the group has a single shard.  ``exchange(blob) -> [blob per rank]``
+        overrides the all-gather (tests)."""
+        if self.R < 2:
+            return False
+        handle, _ = self.index.bounds_export(max_queries)
+        handles = (exchange or self._allgather_bytes)(handle)
+        peers = [handles[self.qg * self.R + r] for r in range(self.R) if r != self.r]
+        self.index.bounds_attach_ipc(peers)
+        self._barrier()
+        return True
+
+    def _barrier(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier(group=self.group)
+
+    def _allgather_bytes(self, blob: bytes) -> list[bytes]:
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.index.device) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        out = torch.empty(self.world * len(blob), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        raw = out.cpu().numpy().tobytes()
+        return [raw[i * len(blob):(i + 1) * len(blob)] for i in range(self.world)]
+
     def add_codes_global(self, codes: np.ndarray):
         """Takes the full [N, M] uint16 code matrix (or any object sliceable by rows) and keeps this rank's block."""
         self.index.add_codes(codes[self.lo:self.hi])

@@ -149,13 +149,14 @@ def kmeans(X: np.ndarray, K: int, iters: int = 25) -> np.ndarray:
         X = np.tile(X, (reps, 1))[:max(K, n)] + np.float32(1e-6) * np.arange(max(K, n), dtype=np.float32)[:, None]
         n = X.shape[0]
     C = X[(np.arange(K, dtype=np.int64) * n) // K].copy()
-    xx = (X * X).sum(1)
-    blk = max(1, (1 << 24) // max(K, 1))
+    blk = max(1, (1 << 20) // max(K, 1))              # 4 MB distance blocks stay in cache
     for _ in range(iters):
         cc = (C * C).sum(1)
+        m2ct = np.ascontiguousarray((np.float32(-2.0) * C).T)
         assign = np.empty(n, np.int64)
         for b in range(0, n, blk):
-            d = xx[b:b + blk, None] - 2.0 * (X[b:b + blk] @ C.T) + cc[None, :]
+            d = X[b:b + blk] @ m2ct                   # |x|^2 is constant per row: argmin of |c|^2 - 2 x.c
+            d += cc[None, :]
             assign[b:b + blk] = d.argmin(1)
         cnt = np.bincount(assign, minlength=K)
         newC = np.zeros_like(C, dtype=np.float64)
