@@ -39,7 +39,8 @@ namespace vaqgpu {
 namespace {
 
 constexpr int T8 = 8;
-constexpr int kQCap = 64;                // every queue: at most 31 pending + 32 pushed by one pass
+constexpr int kQCap = 64;                // level-2 / level-3 queues: at most 31 pending + 32 pushed by one pass
+__host__ __device__ constexpr int q1_cap(int tpi) { return 32 + 32 * tpi; }      // level-1 queue: 31 pending + one stage-1 iteration (TPI tiles)
 
 __device__ __forceinline__ uint32_t half_bits_ru(float x) { return (uint32_t)__half_as_ushort(__float2half_ru(x)); }
 
@@ -54,27 +55,46 @@ __device__ __forceinline__ uint4 lds128_volatile(uint32_t addr) {
   asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 // four 0xFF/0x00 flag bytes -> 4-bit mask (bit i = byte i set)
 __device__ __forceinline__ uint32_t bytes_to_nibble(uint32_t b) { return ((b & 0x01010101u) * 0x10204080u) >> 28; }
 
 __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
 
-// 8-bit mask of the queries whose accumulated lower bound is above the bound stored at `s_thr` (8 x u32, fp16 bits)
-__device__ __forceinline__ uint32_t dead_mask(const __half2 (&acc)[4], uint32_t s_thr) {
-  const uint4 th0 = lds128_volatile(s_thr), th1 = lds128_volatile(s_thr + 16);
-  const uint32_t m0 = __hgt2_mask(acc[0], as_h2(__byte_perm(th0.x, th0.y, 0x5410)));
-  const uint32_t m1 = __hgt2_mask(acc[1], as_h2(__byte_perm(th0.z, th0.w, 0x5410)));
-  const uint32_t m2 = __hgt2_mask(acc[2], as_h2(__byte_perm(th1.x, th1.y, 0x5410)));
-  const uint32_t m3 = __hgt2_mask(acc[3], as_h2(__byte_perm(th1.z, th1.w, 0x5410)));
+// 8-bit mask of the queries whose accumulated lower bound is above the bound stored at `s_thr`: four u32 words,
+// each the fp16 bounds of two queries (2i in the low half, 2i+1 in the high half) — the layout of the accumulators
+__device__ __forceinline__ uint32_t dead_mask_th(const __half2 (&acc)[4], const uint4 th) {
+  const uint32_t m0 = __hgt2_mask(acc[0], as_h2(th.x));
+  const uint32_t m1 = __hgt2_mask(acc[1], as_h2(th.y));
+  const uint32_t m2 = __hgt2_mask(acc[2], as_h2(th.z));
+  const uint32_t m3 = __hgt2_mask(acc[3], as_h2(th.w));
   return bytes_to_nibble(__byte_perm(m0, m1, 0x6420)) | (bytes_to_nibble(__byte_perm(m2, m3, 0x6420)) << 4);
+}
+__device__ __forceinline__ uint32_t dead_mask(const __half2 (&acc)[4], uint32_t s_thr) { return dead_mask_th(acc, lds128_volatile(s_thr)); }
+
+// atomic min on one 16-bit half of a shared-memory word (bit patterns of non-negative halves order like integers)
+__device__ __forceinline__ void atomic_min_half(uint32_t *w, int hi, uint32_t hbits) {
+  uint32_t old = *reinterpret_cast<volatile uint32_t *>(w);
+  while (true) {
+    const uint32_t cur = hi ? (old >> 16) : (old & 0xFFFFu);
+    if (cur <= hbits) return;
+    const uint32_t nw = hi ? ((old & 0xFFFFu) | (hbits << 16)) : ((old & 0xFFFF0000u) | hbits);
+    const uint32_t prev = atomicCAS(w, old, nw);
+    if (prev == old) return;
+    old = prev;
+  }
 }
 
 }  // namespace
 
 // FAST1: the first group has four fields that all start in the row's first 32-bit word (e.g. four 9- or
 // 10-bit subspaces) — stage 1 then needs no per-field word selection and no group-size checks.
-template <int W, bool FAST1>
-__global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid_constant__ AdcFilter16Args a) {
+// TPI = tiles a warp takes per stage-1 iteration.  TPI 1: 32 warps x one row per lane (64 registers per thread).
+// TPI 2: 16 warps x two rows per lane — the same rows in flight per SM, but the two independent gather chains of a
+// lane hide the shared-memory latency by instruction-level parallelism, the per-iteration work (bounds, loop, prefetch
+// addressing) is shared by two tiles, and 128 registers per thread keep the stage-1 program out of the loop.
+template <int W, bool FAST1, int TPI>
+__global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_kernel(const __grid_constant__ AdcFilter16Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int k = a.k;
@@ -83,7 +103,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
 
   const size_t lut_bytes = (size_t)a.lut_stride * T8 * sizeof(__half);       // multiple of 64
   uint32_t *thr_f = reinterpret_cast<uint32_t *>(smem_raw + lut_bytes);      // [8] exact k-th distance bits (fp32)
-  uint32_t *thr_h = thr_f + 8;                                               // [3][8] fp16 bits of RU(thr * scale * margin_l)
+  uint32_t *thr_h = thr_f + 8;                                               // [3][4]: fp16 bits of RU(thr * scale * margin_l), two queries per word
   float *scale_s = reinterpret_cast<float *>(thr_h + 24);                    // [8] scale
   uint32_t *locks = reinterpret_cast<uint32_t *>(scale_s + 8);               // [8]
   uint64_t *lists = reinterpret_cast<uint64_t *>(locks + 8);                 // [8][k] ascending exact keys
@@ -100,7 +120,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     atomicMin(thr_f + t, bits);
     const float v = __uint_as_float(bits) * scale_s[t];
 #pragma unroll
-    for (int l = 0; l < 3; l++) atomicMin(thr_h + l * 8 + t, half_bits_ru(v * margin[l]));
+    for (int l = 0; l < 3; l++) atomic_min_half(thr_h + l * 4 + (t >> 1), t & 1, half_bits_ru(v * margin[l]));
   };
 
   long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
@@ -116,7 +136,8 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     // never survive stage 1 and nothing ever updates the slot
 #pragma unroll
     for (int l = 0; l < 3; l++)
-      thr_h[l * 8 + tid] = (q0 + tid < a.nq) ? half_bits_ru(__uint_as_float(g) * sc * margin[l]) : 0xBC00u;
+      reinterpret_cast<uint16_t *>(thr_h + l * 4)[tid] =
+          (uint16_t)((q0 + tid < a.nq) ? half_bits_ru(__uint_as_float(g) * sc * margin[l]) : 0xBC00u);
     locks[tid] = 0u;
   }
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -131,7 +152,9 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   mbar_wait(bar, 0);
   if (dbg && tid == 0) dbg[1] = clock64();
 
-  // stage-1 program: the first group (<= 4 fields, <= 60 bits, i.e. inside 32-bit words 0..2)
+  // stage-1 program: the first group (<= 4 fields, <= 60 bits, i.e. inside 32-bit words 0..2).  The code is
+  // extracted already multiplied by the 16-byte entry size: (row bits >> (shift - 4)) & (mask << 4); a field that
+  // starts below bit 4 (only field 0 can, in the FAST1 layout) shifts left instead: funnelshift_r(0 : w, 28 + shift).
   const int G1 = min(4, M);
   uint32_t s1_sh[4], s1_mask[4], s1_addr[4];
   bool s1_hi[4];
@@ -139,24 +162,25 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   const uint32_t s_thr_h = smem_u32(thr_h);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const int f = min(i, G1 - 1);
+    const int f = FAST1 ? i : min(i, G1 - 1);
     const uint32_t meta = a.lay.fmeta[f];
-    s1_sh[i] = meta & 31u;
-    s1_mask[i] = meta >> 16;
+    s1_sh[i] = FAST1 ? (((meta & 31u) + 28u) & 31u) : (meta & 31u);          // FAST1: shift - 4 (mod 32)
+    s1_mask[i] = FAST1 ? ((meta >> 16) << 4) : (meta >> 16);
     s1_addr[i] = s_base + a.lay.foff[f] * (T8 * 2);          // shared address of the table
     s1_hi[i] = a.lay.fword[f] != 0;
   }
   const bool two_level = M > 8;
   const int F2 = two_level ? 8 : M;
 
-  uint32_t *q1 = queues + (size_t)warp * (3 * kQCap);
-  uint32_t *q2 = q1 + kQCap;
+  uint32_t *q1 = queues + (size_t)warp * (q1_cap(TPI) + 2 * kQCap);
+  uint32_t *q2 = q1 + q1_cap(TPI);
   uint32_t *q3 = q2 + kQCap;
   int q1n = 0, q2n = 0, q3n = 0;
-  // Bounds only tighten when the exact level runs.  Waiting for 32 pending rows per warp is right in steady state
-  // (full lanes) but on a short chunk most of it would be scanned under the seed bound: the first exact passes of
-  // a warp run as soon as 4, 8, 16 rows are pending (bias 28 -> 24 -> 16 -> 0).
-  int q3_bias = 28;
+  // Bounds only tighten when the exact level runs.  Waiting for 32 pending rows per queue is right in steady state
+  // (full lanes), but under the seed bound only ~0.3 % of the rows reach the exact level: a warp would scan half of a
+  // 125 K-row chunk before its first exact pass.  So the deep queues start eager — the exact level runs as soon as
+  // one row is pending (four times), the full lower bound as soon as four are — and the thresholds double up to 32.
+  int q2_need = 4, q3_need = 1, q3_eager = 4;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   const int64_t tile_begin = a.tile_lo + (int64_t)chunk * a.chunk_tiles;
@@ -164,12 +188,17 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
   const int64_t row_base = tile_begin << 5;
   const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
 
-  int64_t tl = tile_begin + warp;
-  uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-  const uint4 *pnext = a.codes + ((size_t)(tl + nwarps) * W) * kTileRows + lane;     // tile whose words `nxt` holds
+  // this warp's tiles: warp, warp + nwarps, ... ; an iteration takes TPI consecutive ones of them, the next TPI are
+  // prefetched in registers
+  uint4 cur[TPI], nxt[TPI];
   const size_t pstep = (size_t)nwarps * W * kTileRows;
-  if (tl < tile_end) cur = ldg_stream_u4(pnext - pstep);
-  if (tl + nwarps < tile_end) nxt = ldg_stream_u4(pnext);
+  const uint4 *pnext = a.codes + ((size_t)(tile_begin + warp) * W) * kTileRows + lane + TPI * pstep;     // first tile of `nxt`
+#pragma unroll
+  for (int u = 0; u < TPI; u++) {
+    cur[u] = nxt[u] = make_uint4(0, 0, 0, 0);
+    if (tile_begin + warp + u * nwarps < tile_end) cur[u] = ldg_stream_u4(pnext - (TPI - u) * pstep);
+    if (tile_begin + warp + (TPI + u) * nwarps < tile_end) nxt[u] = ldg_stream_u4(pnext + u * pstep);
+  }
   int refresh = 0;
   const uint32_t rows_here = (uint32_t)(min(a.n_rows, tile_end << 5) - row_base);    // valid rows of this chunk
 
@@ -271,24 +300,82 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
     __syncthreads();
   }
   if (dbg && tid == 0) dbg[2] = clock64();
+  // 32-bit loop state: tile index relative to the chunk (a chunk has at most 32768 tiles)
+  int it = warp;
+  const int n_it = (int)(tile_end - tile_begin);
+  const uint32_t q1_s = smem_u32(q1);
   int dbg_tail = 0;
 
   while (true) {
-    const bool more = tl < tile_end;
-    if (dbg && !more && !dbg_tail && tid == 0) { dbg[3] = clock64(); dbg_tail = 1; }
+    if (dbg && it >= n_it && !dbg_tail && tid == 0) { dbg[3] = clock64(); dbg_tail = 1; }
+    // ---- what next: a queue that holds a full pass goes first (deepest level first: it feeds nothing further and
+    // frees the bounds), otherwise stage 1 streams tiles until the level-1 queue fills, at the end everything drains
     int level = 0, take = 0;
-    if (((q1n | q2n | (q3n + q3_bias)) >= 32) || !more) {           // rarely true: keep the common path to one test
-      if (q3n + q3_bias >= 32) { level = 3; take = min(q3n, 32); q3_bias = max(0, 2 * q3_bias - 32); }
-      else if (q2n >= 32) { level = 2; take = 32; }
-      else if (q1n >= 32) { level = 1; take = 32; }
-      else if (!more) {
-        if (q1n > 0) { level = 1; take = q1n; }
-        else if (q2n > 0) { level = 2; take = q2n; }
-        else if (q3n > 0) { level = 3; take = q3n; }
-        else break;
-      }
+    if (q3n >= q3_need) { level = 3; take = min(q3n, 32); if (q3_eager > 0) q3_eager--; else q3_need = min(32, 2 * q3_need); }
+    else if (q2n >= q2_need) { level = 2; take = min(q2n, 32); q2_need = min(32, 2 * q2_need); }
+    else if (q1n >= 32) { level = 1; take = 32; }
+    else if (it < n_it) {
+      // ---- stage 1: tight loop over this warp's tiles ---------------------------------------------------------
+      do {
+        uint4 w[TPI];
+#pragma unroll
+        for (int u = 0; u < TPI; u++) { w[u] = cur[u]; cur[u] = nxt[u]; }
+        pnext += TPI * pstep;
+#pragma unroll
+        for (int u = 0; u < TPI; u++)
+          if (it + (2 * TPI + u) * nwarps < n_it) nxt[u] = ldg_stream_u4(pnext + u * pstep);
+        if (((++refresh) & (TPI == 2 ? 15 : 31)) == 0 && lane < T8 && q0 + lane < a.nq) {
+          // pick up bounds published by other row chunks of this query tile (and, row-sharded, by other GPUs)
+          const uint32_t g = *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane);
+          if (g < *reinterpret_cast<volatile uint32_t *>(thr_f + lane)) publish_bound(lane, g);
+        }
+        const uint4 th = lds128_volatile(s_thr_h);      // the eight stage-1 bounds, two per word like the accumulators
+        unsigned sb[TPI];
+#pragma unroll
+        for (int u = 0; u < TPI; u++) {
+          const uint4 w0 = w[u];
+          __half2 acc[4];
+#pragma unroll
+          for (int i1 = 0; i1 < 4; i1++) {
+            if (FAST1 || i1 < G1) {
+              uint4 v;
+              if constexpr (FAST1) {
+                // field 0 starts at bit 0 (pair 0 : w0.x), the others at bit >= 4 inside word 0 (pair w0.x : w0.y)
+                const uint32_t c16 = (i1 == 0 ? __funnelshift_r(0u, w0.x, s1_sh[0]) : __funnelshift_r(w0.x, w0.y, s1_sh[i1])) & s1_mask[i1];
+                v = lds128(s1_addr[i1] + c16);
+              } else {
+                const uint32_t lo = s1_hi[i1] ? w0.y : w0.x, hi = s1_hi[i1] ? w0.z : w0.y;
+                const uint32_t code = __funnelshift_r(lo, hi, s1_sh[i1]) & s1_mask[i1];
+                v = lds128(s1_addr[i1] + code * (T8 * 2));
+              }
+              if (i1 == 0) { acc[0] = as_h2(v.x); acc[1] = as_h2(v.y); acc[2] = as_h2(v.z); acc[3] = as_h2(v.w); }
+              else {
+                acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
+                acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+              }
+            }
+          }
+          sb[u] = ~dead_mask_th(acc, th) & 0xFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < TPI; u++) {
+          const int itu = it + u * nwarps;
+          const uint32_t rel = ((uint32_t)itu << 5) + lane;
+          if (itu >= n_it || (itu == n_it - 1 && rel >= rows_here)) sb[u] = 0u;      // past the chunk / the partial last tile of the index
+          // compact the rows that still have a live query into the warp's queue
+          const unsigned m = __ballot_sync(0xffffffffu, sb[u] != 0);
+          if (sb[u]) sts32(q1_s + (uint32_t)(q1n + __popc(m & lt_mask)) * 4u, (rel << 8) | sb[u]);
+          q1n += __popc(m);
+        }
+        it += TPI * nwarps;
+      } while (it < n_it && q1n < 32);
+      continue;
     }
-    if (level) {
+    else if (q1n > 0) { level = 1; take = q1n; }
+    else if (q2n > 0) { level = 2; take = q2n; }
+    else if (q3n > 0) { level = 3; take = q3n; }
+    else break;
+    {
       // ---- 32 queued rows, one per lane (single code site for the three levels) -----------------------
       __syncwarp();
       const bool active = lane < take;
@@ -349,7 +436,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
           acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
           acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
         }
-        mask &= ~dead_mask(acc, s_thr_h + level * 32);
+        mask &= ~dead_mask(acc, s_thr_h + level * 16);
         const unsigned m = __ballot_sync(0xffffffffu, mask != 0);
         const bool to_q2 = level == 1 && two_level;
         if (mask) {
@@ -418,43 +505,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
           }
         }
       }
-      continue;
     }
-
-    // ---- stage 1 on one tile ---------------------------------------------------------------------------
-    const uint4 w0 = cur;
-    cur = nxt;
-    pnext += pstep;
-    if (tl + 2 * (int64_t)nwarps < tile_end) nxt = ldg_stream_u4(pnext);
-    if (((++refresh) & 31) == 0 && lane < T8 && q0 + lane < a.nq) {
-      // pick up bounds published by other row chunks of this query tile
-      const uint32_t g = *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane);
-      if (g < *reinterpret_cast<volatile uint32_t *>(thr_f + lane)) publish_bound(lane, g);
-    }
-    __half2 acc[4];
-#pragma unroll
-    for (int i1 = 0; i1 < 4; i1++) {
-      if (FAST1 || i1 < G1) {
-        const uint32_t lo = (!FAST1 && s1_hi[i1]) ? w0.y : w0.x, hi = (!FAST1 && s1_hi[i1]) ? w0.z : w0.y;
-        const uint32_t code = __funnelshift_r(lo, hi, s1_sh[i1]) & s1_mask[i1];
-        const uint4 v = lds128(s1_addr[i1] + code * (T8 * 2));
-        if (i1 == 0) { acc[0] = as_h2(v.x); acc[1] = as_h2(v.y); acc[2] = as_h2(v.z); acc[3] = as_h2(v.w); }
-        else {
-          acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
-          acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
-        }
-      }
-    }
-    const uint32_t rel = ((uint32_t)(tl - tile_begin) << 5) + lane;
-    unsigned sb = ~dead_mask(acc, s_thr_h) & 0xFFu;
-    if (tl == tile_end - 1 && rel >= rows_here) sb = 0u;      // only the last tile of the index can be partial
-    {
-      // compact the rows that still have a live query into the warp's queue
-      const unsigned m = __ballot_sync(0xffffffffu, sb != 0);
-      if (sb) q1[q1n + __popc(m & lt_mask)] = (rel << 8) | sb;
-      q1n += __popc(m);
-    }
-    tl += nwarps;
   }
 
   // ---- CTA epilogue: publish this (query tile, chunk)'s keys -----------------------------------------
@@ -469,31 +520,39 @@ __global__ void __launch_bounds__(1024, 1) adc_filter16_scan_kernel(const __grid
 }
 
 size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads) {
-  const int nwarps = threads / 32;
+  const int nwarps = threads / 32, tpi = threads <= 512 ? 2 : 1;
   size_t b = (size_t)lut_stride * T8 * 2 + 6 * 32;          // tables + bounds/scales/locks
   b += ((size_t)T8 * k + 1) * sizeof(uint64_t);
-  b += (size_t)nwarps * (3 * kQCap) * sizeof(uint32_t);
+  b += (size_t)nwarps * (q1_cap(tpi) + 2 * kQCap) * sizeof(uint32_t);
   return b;
 }
 
-template <int W, bool FAST1>
-static cudaError_t launch16_wf(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
+template <int W, bool FAST1, int TPI>
+static cudaError_t launch16_wft(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
   static SmemOptIn optin;
   {
-    cudaError_t e = optin.ensure(adc_filter16_scan_kernel<W, FAST1>, smem_bytes);
+    cudaError_t e = optin.ensure(adc_filter16_scan_kernel<W, FAST1, TPI>, smem_bytes);
     if (e != cudaSuccess) return e;
   }
   const int64_t nt = a.tile_hi - a.tile_lo;
   if (nt <= 0) return cudaSuccess;
   dim3 grid((unsigned)((a.nq + T8 - 1) / T8), (unsigned)((nt + a.chunk_tiles - 1) / a.chunk_tiles));
-  adc_filter16_scan_kernel<W, FAST1><<<grid, threads, smem_bytes, st>>>(a);
+  adc_filter16_scan_kernel<W, FAST1, TPI><<<grid, threads, smem_bytes, st>>>(a);
   return cudaGetLastError();
+}
+
+// threads <= 512: two tiles per warp and iteration (TPI 2); more threads: one
+template <int W, bool FAST1>
+static cudaError_t launch16_wf(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
+  return threads <= 512 ? launch16_wft<W, FAST1, 2>(a, threads, smem_bytes, st) : launch16_wft<W, FAST1, 1>(a, threads, smem_bytes, st);
 }
 
 template <int W>
 static cudaError_t launch16_w(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
+  // FAST1: four leading fields that all start in the row's first 32-bit word, the first one at least 4 bits wide
   bool fast1 = a.lay.M >= 4;
   for (int f = 0; f < 4 && fast1; f++) fast1 = a.lay.fword[f] == 0;
+  if (fast1) fast1 = (a.lay.fmeta[1] & 31u) >= 4u;
   return fast1 ? launch16_wf<W, true>(a, threads, smem_bytes, st) : launch16_wf<W, false>(a, threads, smem_bytes, st);
 }
 
