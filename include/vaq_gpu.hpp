@@ -10,6 +10,16 @@
 // hands its public members to loadModel().  Matrices are passed as row-major float pointers — exactly
 // RowMatrixXf::data() (utils/Types.hpp:14-18) — so the shim itself does not need Eigen.
 //
+// With Eigen included first (as every reference caller does, examples/demo_vaq.cpp:11-14) the classes also carry the
+// reference's exact Eigen-typed signatures (VAQ.hpp:93-114) —
+//     void encode(const RowMatrixXf &XTrain);
+//     LabelDistVecF search(const RowMatrixXf &XTest, const int k, bool verbose = false);
+//     LabelDistVecF refine(const RowMatrixXf &XTest, const LabelDistVecF &answersIn, const RowMatrixXf &XTrain, const int k);
+// — and `adopt(const RefVAQ &)`, which takes the trained state straight out of a reference `VAQ` object (all its
+// members are public), so the query phase of examples/demo_vaq.cpp:337-345 compiles unchanged against this header
+// (tests/cpp/demo_sequence_check.cpp does exactly that).  If the reference's utils/Types.hpp was included, its
+// LabelDistVecF / IdxDistPair are used as the result types, so results flow into the reference's own helpers.
+//
 // Error behaviour: the reference prints and calls exit(0)/assert(false) (VAQ.cpp:64-78, 1263-1266); the
 // shim throws std::runtime_error carrying vaqgpu_last_error().  There is no CPU fallback.
 #pragma once
@@ -21,8 +31,17 @@
 
 #include "vaqgpu.h"
 
+#if defined(EIGEN_WORLD_VERSION) && !defined(VAQGPU_NO_EIGEN)
+#define VAQGPU_HAVE_EIGEN 1
+#endif
+
 namespace vaqgpu {
 
+#ifdef TYPES_HPP_
+// the reference's own result types (utils/Types.hpp:42-51, 98-104)
+using LabelDistVecF = ::LabelDistVecF;
+using IdxDistPair = ::IdxDistPair;
+#else
 // utils/Types.hpp:98-104
 struct LabelDistVecF {
   std::vector<int> labels;
@@ -33,8 +52,12 @@ struct IdxDistPair {
   int idx;
   uint32_t dist;
 };
+#endif
 using bitv = std::vector<uint64_t>;        // BitVector.hpp:13
 using bitvectors = std::vector<bitv>;      // BitVector.hpp:19
+#ifdef VAQGPU_HAVE_EIGEN
+using RowMatrixXf = Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>;      // utils/Types.hpp:14-16
+#endif
 
 inline void check(int rc) {
   if (rc != VAQGPU_OK) throw std::runtime_error(std::string("vaqgpu: ") + vaqgpu_last_error());
@@ -138,6 +161,63 @@ class VAQ {
   }
 
   vaqgpu_t *handle() { return need(); }
+
+#ifdef VAQGPU_HAVE_EIGEN
+  // ---- the reference's Eigen-typed signatures (VAQ.hpp:93-114) ----------------------------------------------------
+  // VAQ::encode (VAQ.cpp:663): rows already projected (train() projects its argument in place, VAQ.cpp:294)
+  void encode(const RowMatrixXf &XTrain) { encode(XTrain.data(), (int64_t)XTrain.rows()); }
+
+  // VAQ::search (VAQ.cpp:776-847)
+  LabelDistVecF search(const RowMatrixXf &XTest, const int k, bool verbose = false) {
+    const int D = mSubsLen * mHighestSubs;
+    if ((int)XTest.cols() == D) return search(XTest.data(), (int)XTest.rows(), k, verbose);
+    if ((int)XTest.cols() > D) throw std::runtime_error("vaqgpu::VAQ::search: XTest has more columns than the model's padded dimensionality");
+    RowMatrixXf padded = RowMatrixXf::Zero(XTest.rows(), D);          // the demo pads its matrices the same way (demo_vaq.cpp:74-76,281)
+    padded.leftCols(XTest.cols()) = XTest;
+    return search(padded.data(), (int)padded.rows(), k, verbose);
+  }
+
+  // VAQ::refine (VAQ.cpp:849-876)
+  LabelDistVecF refine(const RowMatrixXf &XTest, const LabelDistVecF &answersIn, const RowMatrixXf &XTrain, const int k) {
+    if (XTest.cols() != XTrain.cols()) throw std::runtime_error("vaqgpu::VAQ::refine: XTest / XTrain column mismatch");
+    return refine(XTest.data(), (int)XTest.rows(), answersIn, XTrain.data(), (int64_t)XTrain.rows(), (int)XTrain.cols(), k);
+  }
+
+  // Take over a trained (and, optionally, encoded / clustered) reference `VAQ` — any type with the reference's public
+  // members (VAQ.hpp:51-84): mSubsLen, mHighestSubs, mBitsAlloc, mCentroidsPerSubs, mEigenVectors, the method knobs,
+  // mCodebook when encode() already ran on the host, and clusterTI()'s outputs when the method string asks for TI.
+  template <class RefVAQ>
+  void adopt(const RefVAQ &v, bool with_codebook = true) {
+    std::vector<float> cent;
+    for (int s = 0; s < v.mHighestSubs; s++) {
+      const RowMatrixXf c = v.mCentroidsPerSubs[(size_t)s];           // row-major [K_s x L]
+      cent.insert(cent.end(), c.data(), c.data() + c.size());
+    }
+    const RowMatrixXf eig = v.mEigenVectors.real();                   // VAQ.hpp:57, consumed by search() at VAQ.cpp:777
+    const int D = v.mSubsLen * v.mHighestSubs;
+    loadModel(v.mSubsLen, v.mHighestSubs, v.mBitsAlloc.data(), cent.data(),
+              (eig.rows() == D && eig.cols() == D) ? eig.data() : nullptr);
+    mBitBudget = v.mBitBudget; mSubspaceNum = v.mSubspaceNum; mMinBitsPerSubs = v.mMinBitsPerSubs; mMaxBitsPerSubs = v.mMaxBitsPerSubs;
+    mPercentVarExplained = v.mPercentVarExplained;
+    mMethods = (int)v.mMethods; mVisit = v.mVisit; mTIClusterNum = v.mTIClusterNum;
+    if (with_codebook && v.mCodebook.rows() > 0) {
+      if ((int)v.mCodebook.cols() != v.mHighestSubs) throw std::runtime_error("vaqgpu::VAQ::adopt: mCodebook has the wrong number of columns");
+      setCodebook(v.mCodebook.data(), (int64_t)v.mCodebook.rows());  // RowMatrix<uint16_t>, utils/Types.hpp:31
+      if ((mMethods & TI) && v.mTIClusters.rows() > 0) {
+        const int C = (int)v.mTIClusters.rows();
+        std::vector<int64_t> start((size_t)C), size((size_t)C);
+        std::vector<int32_t> members;
+        for (int c = 0; c < C; c++) {
+          start[(size_t)c] = v.mClusterMembersStartIdx[(size_t)c];
+          size[(size_t)c] = (int64_t)v.mTIClustersMember[(size_t)c].size();
+          members.insert(members.end(), v.mTIClustersMember[(size_t)c].begin(), v.mTIClustersMember[(size_t)c].end());
+        }
+        const RowMatrixXf cl = v.mTIClusters;
+        setClusters(cl.data(), C, (int)cl.cols(), start.data(), size.data(), members.data());
+      }
+    }
+  }
+#endif  // VAQGPU_HAVE_EIGEN
 
  private:
   vaqgpu_t *need() {

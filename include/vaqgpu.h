@@ -99,6 +99,12 @@ int vaqgpu_row_bytes(const vaqgpu_t *h, int32_t *bytes);
 /* Unpack rows [row0, row0+n) back to [n x M] uint16 (round-trip check against mCodebook). */
 int vaqgpu_get_codes_u16(vaqgpu_t *h, int64_t row0, int64_t n, uint16_t *out);
 
+/* Storage order of the packed matrix: out[i] = original (arrival) index of the row stored at position srow0 + i.
+ * The library re-orders rows inside windows of 4096 so that the eight rows a quarter-warp gathers for hit different
+ * shared-memory banks (csrc/layout.cu); ids, codes and results are always expressed in the original order — this
+ * call exists for diagnostics and tests. */
+int vaqgpu_get_row_order(vaqgpu_t *h, int64_t srow0, int64_t n, uint32_t *out);
+
 /* replaces VAQ::CreateLUT (VAQ.hpp:128-167).  q_proj: host [nq x D] projected queries;
  * lut_out: host [nq x sum_s 2^bits[s]], table s at offset sum_{t<s} 2^bits[t]. */
 int vaqgpu_build_lut(vaqgpu_t *h, const float *q_proj, int32_t nq, float *lut_out);
@@ -158,7 +164,8 @@ int vaqgpu_last_timings(const vaqgpu_t *h, float ms[4]);
  * [2]=LUT entries per query resident in shared memory, [3]=LUT entries spilled to L2, [4]=dynamic smem
  * bytes, [5]=uint4 words per row, [6]=kernel launches of the last search, [7]=queries per launch,
  * [8]=queries per CTA (tile width T), [9]=scan kernel (1 = lane-per-row, 2 = filter-and-refine on fp32
- * tables, 3 = filter-and-refine on fp16 lower-bound tables). */
+ * tables, 3 = filter-and-refine on fp16 lower-bound tables), [10]=1 when the rows are in the conflict-aware order
+ * (csrc/layout.cu), [11]=microseconds spent re-ordering so far. */
 int vaqgpu_last_config(const vaqgpu_t *h, int32_t cfg[12]);
 
 /* ---- BitVecEngine Hamming index ---------------------------------------- */

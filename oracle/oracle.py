@@ -40,6 +40,30 @@ def build(ref: bool | None = None) -> None:
     subprocess.run(["make", "-s", "-C", str(HERE), f"REF={REFERENCE_ROOT}", "-j8", *targets], check=True)
 
 
+DEMO_CHECK_SRC = HERE.parent / "tests" / "cpp" / "demo_sequence_check.cpp"
+DEMO_CHECK_BIN = HERE.parent / "tests" / "cpp" / "_bin" / "demo_sequence_check"
+
+
+def build_demo_check() -> Path | None:
+    """tests/cpp/demo_sequence_check.cpp — the reference demo's query phase (examples/demo_vaq.cpp:337-345, verbatim)
+    compiled against include/vaq_gpu.hpp with the reference's own headers (VAQ.hpp, utils/Experiment.hpp, vendored
+    Eigen) and linked with the compiled reference + libvaqgpu.so.  Needs the reference tree (headers are never copied):
+    returns None when it is not mounted; the binary is git-ignored and travels to the GPU box like the other built files."""
+    ref = REFERENCE_ROOT
+    if not ((ref / "bitvecengine" / "VAQ.hpp").exists() and (ref / "external" / "eigen" / "Eigen" / "Core").exists() and REF_SO.exists()):
+        return DEMO_CHECK_BIN if DEMO_CHECK_BIN.exists() else None
+    root = HERE.parent
+    if DEMO_CHECK_BIN.exists() and DEMO_CHECK_BIN.stat().st_mtime > max(DEMO_CHECK_SRC.stat().st_mtime, (root / "include" / "vaq_gpu.hpp").stat().st_mtime,
+                                                                       (root / "include" / "vaqgpu.h").stat().st_mtime):
+        return DEMO_CHECK_BIN
+    DEMO_CHECK_BIN.parent.mkdir(exist_ok=True)
+    subprocess.run(["g++", "-std=c++14", "-O1", "-mavx2", "-mfma", "-fopenmp", "-w", "-I", str(root / "include"), "-I", str(HERE / "stubs"),
+                    "-I", str(ref / "external" / "eigen"), "-I", str(ref / "bitvecengine"), str(DEMO_CHECK_SRC), "-o", str(DEMO_CHECK_BIN),
+                    "-L", str(root / "vaq_b200"), "-lvaqgpu", f"-Wl,-rpath,{root / 'vaq_b200'}",
+                    "-L", str(HERE / "_ref"), "-lvaq_ref", f"-Wl,-rpath,{HERE / '_ref'}", "-Wl,--allow-multiple-definition"], check=True)
+    return DEMO_CHECK_BIN
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

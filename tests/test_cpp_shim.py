@@ -64,3 +64,58 @@ def test_shim_search_matches_oracle(tmp_path):
         assert np.array_equal(lab, want_lab) and bitwise_equal(dis, want_dis)
     assert_knn_equiv(ea_lab, ea_dis, g["lab_ea"], g["dis_ea"], what="shim EA vs reference")
     assert_knn_equiv(hp_lab, hp_dis, g["lab_heap"], g["dis_heap"], what="shim HEAP vs reference")
+
+
+# ---- the reference demo's query phase, compiled unchanged against the shim's Eigen-typed signatures ---------------
+
+def build_demo_binary(tmp_path: Path) -> Path:
+    """examples/demo_vaq.cpp:337-345 verbatim inside tests/cpp/demo_sequence_check.cpp, built with the reference's own
+    headers + include/vaq_gpu.hpp (oracle.build_demo_check); on the GPU box, where the reference tree is not mounted,
+    the binary built here travels with the snapshot."""
+    from vaq_b200 import build as vb
+    vb.build()
+    exe = orc.build_demo_check()
+    if exe is None:
+        pytest.skip("reference headers not mounted and no prebuilt binary")
+    return exe
+
+
+def write_demo_input(path: Path, g, m):
+    X, Qraw = g["X"], g["Qraw"]
+    hdr = np.array([m.L, m.M, Qraw.shape[0], Qraw.shape[1], g["codes"].shape[0], 1], np.int32)
+    with open(path, "wb") as f:
+        f.write(hdr.tobytes()); f.write(m.bits.astype(np.int32).tobytes()); f.write(m.cent_flat.tobytes())
+        f.write(np.ascontiguousarray(g["eig"], np.float32).tobytes())
+        f.write(np.ascontiguousarray(g["codes"], np.uint16).tobytes())
+        f.write(np.ascontiguousarray(Qraw, np.float32).tobytes()); f.write(np.ascontiguousarray(X, np.float32).tobytes())
+
+
+def test_demo_query_phase_compiles_unchanged(tmp_path):
+    from vaq_b200 import _lib
+    exe = build_demo_binary(tmp_path)
+    g = load_golden("vaq_small_a")
+    m, _ = golden_model(g)
+    write_demo_input(tmp_path / "in.bin", g, m)
+    r = subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), "--k", "10", "--refine", "0,40"],
+                       capture_output=True, text=True)
+    if _lib.device_count() == 0:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr, (r.returncode, r.stderr)
+        return
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(tmp_path / "out.bin", np.uint8)
+    nq, k = g["Qraw"].shape[0], 10
+    # refine = 0: plain search with k = 10 on raw queries (device-side projection: tolerance-only, Appendix B rule 2)
+    cnt = int(raw[:4].view(np.int32)[0]); assert cnt == nq * k
+    lab = raw[4:4 + 4 * cnt].view(np.int32).reshape(nq, k); dis = raw[4 + 4 * cnt:4 + 8 * cnt].view(np.float32).reshape(nq, k)
+    want_lab, want_dis = orc.Port().search_lex(m, g["codes"], g["Q"], k)
+    np.testing.assert_allclose(dis, want_dis, rtol=2e-4)
+    assert (lab == want_lab).mean() > 0.95
+    # refine = 40: search k = 40, exact re-rank to 10 against the raw rows (VAQ::refine, VAQ.cpp:849-876)
+    off = 4 + 8 * cnt
+    cnt2 = int(raw[off:off + 4].view(np.int32)[0]); assert cnt2 == nq * k
+    lab2 = raw[off + 4:off + 4 + 4 * cnt2].view(np.int32).reshape(nq, k)
+    dis2 = raw[off + 4 + 4 * cnt2:off + 4 + 8 * cnt2].view(np.float32).reshape(nq, k)
+    l40, _ = orc.Port().search_lex(m, g["codes"], g["Q"], 40)
+    rl, rd = orc.Port().refine(g["Qraw"], l40, g["X"], k)
+    np.testing.assert_allclose(dis2, rd, rtol=1e-4)
+    assert (lab2 == rl).mean() > 0.95

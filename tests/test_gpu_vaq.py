@@ -477,3 +477,61 @@ def test_search_many_subspaces_fp16_path(port, M, bits_of):
     ix.search(Q, 10, EA | PROJECTED)
     assert ix.last_config()["scan_kernel"] == 3
     ix.close()
+
+
+# ---- conflict-aware row order (csrc/layout.cu) ---------------------------------------------------------------------
+
+def quarter_conflicts(codes, order, nf=4):
+    """average over quarter-warps (8 consecutive storage rows) and stage-1 fields of the maximum multiplicity of
+    `code mod 8` — the number of shared-memory wavefronts a 128-bit gather of that field costs."""
+    res = (codes[order][:, :nf] & 7).astype(np.int64)
+    n8 = (res.shape[0] // 8) * 8
+    r = res[:n8].reshape(-1, 8, nf)
+    onehot = (r[..., None] == np.arange(8)[None, None, None, :]).sum(1)          # [groups, nf, 8]
+    return float(onehot.max(2).mean())
+
+
+def test_conflict_aware_layout_is_invisible_and_effective(port):
+    from vaq_b200.index import EA, PROJECTED
+    rng = np.random.default_rng(31)
+    bits = [9, 9, 9, 9, 8, 8, 7, 7, 7, 7, 6, 6]
+    m = random_model(rng, len(bits), 2, bits)
+    n1, n2 = 30000, 11111
+    codes = random_codes(rng, m, n1 + n2)
+    Q = rng.standard_normal((20, m.D)).astype(np.float32)
+    ix = make_index(m, codes=codes[:n1])
+    assert np.array_equal(ix.get_row_order(), np.arange(n1))                      # arrival order until the first search
+    check_search(port, m, codes[:n1], Q, 10, EA, ix=ix)
+    assert ix.last_config()["conflict_aware_layout"] == 1
+    order = ix.get_row_order()
+    assert np.array_equal(np.sort(order), np.arange(n1))                          # a permutation ...
+    assert np.array_equal(order // 4096, np.arange(n1) // 4096)                   # ... inside windows of 4096 rows
+    before, after = quarter_conflicts(codes[:n1], np.arange(n1)), quarter_conflicts(codes[:n1], order)
+    assert before > 2.4 and after < 1.6, (before, after)
+    assert np.array_equal(ix.get_codes(), codes[:n1])                             # codes read back in the original order
+    assert np.array_equal(ix.get_codes(4000, 300), codes[4000:4300])
+    # rows appended later: the partially filled window is planned again, everything stays consistent
+    ix.add_codes(codes[n1:])
+    check_search(port, m, codes, Q, 10, EA, ix=ix)
+    order = ix.get_row_order()
+    assert np.array_equal(np.sort(order), np.arange(n1 + n2)) and np.array_equal(order // 4096, np.arange(n1 + n2) // 4096)
+    assert quarter_conflicts(codes, order) < 1.6
+    assert np.array_equal(ix.get_codes(), codes)
+    ix.close()
+
+
+def test_layout_restored_for_ti_after_plain_searches(port):
+    """An EA search re-orders the rows; vaqgpu_set_clusters afterwards must see the arrival order again."""
+    from vaq_b200.index import EA, PROJECTED, SQRT, TI
+    g = load_golden("vaq_small_a")
+    m, _ = golden_model(g)
+    grouped = g["ti_codes_grouped"]
+    ix = make_index(m, codes=grouped)
+    ix.search(g["Q"], 10, EA | PROJECTED)                                         # triggers the re-ordering
+    assert ix.last_config()["conflict_aware_layout"] == 1
+    ix.set_clusters(g["ti_clusters"], g["ti_start_idx"].astype(np.int64), g["ti_sizes"].astype(np.int64), g["ti_members"].astype(np.int32))
+    assert np.array_equal(ix.get_row_order(), np.arange(grouped.shape[0]))
+    ix.set_visit(0.25)
+    lab, dis = ix.search(g["Q"], int(g["k"]), TI | EA | SQRT | PROJECTED)
+    assert_knn_equiv(lab, dis, g["ti_lab_v25"], g["ti_dis_v25"], what="TI visit 0.25 after layout restore")
+    ix.close()

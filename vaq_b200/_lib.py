@@ -45,6 +45,7 @@ PROTOTYPES = {
     "vaqgpu_num_rows": (C.c_int, [_p, C.POINTER(_i64)]),
     "vaqgpu_row_bytes": (C.c_int, [_p, C.POINTER(_i32)]),
     "vaqgpu_get_codes_u16": (C.c_int, [_p, _i64, _i64, _p]),
+    "vaqgpu_get_row_order": (C.c_int, [_p, _i64, _i64, _p]),
     "vaqgpu_build_lut": (C.c_int, [_p, _p, _i32, _p]),
     "vaqgpu_search": (C.c_int, [_p, _p, _i32, _i32, _u32, _p, _p]),
     "vaqgpu_search_device": (C.c_int, [_p, _p, _i32, _i32, _u32, _p, _p, _p]),

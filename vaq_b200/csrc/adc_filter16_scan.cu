@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
             if (__all_sync(0xffffffffu, !act || (dist > thr))) { alive = false; break; }
           }
           if (!alive) continue;
-          const uint64_t key = act ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
+          // keys carry the ORIGINAL row index (the storage order is conflict-aware, layout.cu): canonical (distance, id) order
+          const uint64_t key = act ? make_key_f32(dist, a.rowid ? (int32_t)__ldg(a.rowid + row) : (int32_t)row) : kEmptyKey;
           const uint64_t kth0 = act ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
           unsigned m = __ballot_sync(0xffffffffu, key < kth0);
           while (m) {

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(1024, 1) adc_filter_scan_kernel(const __grid_c
           }
           q2n += __popc(m);
         } else {
-          const uint64_t key = active ? make_key_f32(dist, (int32_t)row) : kEmptyKey;
+          const uint64_t key = active ? make_key_f32(dist, a.rowid ? (int32_t)__ldg(a.rowid + row) : (int32_t)row) : kEmptyKey;
           const uint64_t kth0 = active ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
           unsigned m = __ballot_sync(0xffffffffu, key < kth0);
           while (m) {

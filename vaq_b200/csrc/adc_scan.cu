@@ -131,7 +131,7 @@ __global__ void adc_scan_kernel(const __grid_constant__ AdcScanArgs a) {
       float dist = 0.f;
       const bool alive = score_tile<W>(cur, a, slut, gspill, thr, lane_dead, ea, dist);
       if (alive) {
-        const uint64_t key = lane_dead ? kEmptyKey : make_key_f32(dist, row);
+        const uint64_t key = lane_dead ? kEmptyKey : make_key_f32(dist, a.rowid ? (int32_t)__ldg(a.rowid + row) : row);
         unsigned m = __ballot_sync(0xffffffffu, key < thrkey);
         if (m) {
           uint64_t kth = thrkey;

@@ -9,6 +9,7 @@ constexpr int kMaxSubspaces = 128;   // M
 constexpr int kMaxRowWords = 32;     // 32-bit words per packed row (<= 1024 bits)
 constexpr int kTileRows = 32;        // rows per tile == warp width
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kLayoutWin = 4096;     // rows per window of the conflict-aware row order (layout.cu); a multiple of kTileRows
 
 // fmeta bit layout: [4:0] shift inside the starting 32-bit word, [5] table spilled to
 // global/L2, [31:16] value mask ((1<<bits)-1).
@@ -208,6 +209,7 @@ struct AdcScanArgs {
   const int2 *ranges;        // [nq][max_ranges] (row_begin, row_end) in visiting order
   const int32_t *n_ranges;   // [nq]
   int32_t max_ranges;
+  const uint32_t *rowid;     // original row index of each storage row (layout.cu), or NULL = identity
   ScanLayout lay;
 };
 
@@ -230,6 +232,7 @@ struct AdcFilterArgs {
   uint32_t *thr_global;      // [nq] float bits of the best known k-th distance (0xFFFFFFFF = none)
   PeerBounds peers;          // the same array on the other row shards (n = 0: single shard)
   int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
+  const uint32_t *rowid;     // original row index of each storage row (layout.cu), or NULL = identity
   ScanLayout lay;
 };
 size_t adc_filter_smem_bytes(int smem_lut_floats, int T, int k, int threads);
@@ -251,6 +254,7 @@ struct AdcFilter16Args {
   uint32_t *thr_global;
   PeerBounds peers;          // the same array on the other row shards (n = 0: single shard)
   int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
+  const uint32_t *rowid;     // original row index of each storage row (layout.cu), or NULL = identity
   long long *dbg;            // development: per-CTA phase clocks (NULL = off)
   ScanLayout lay;
 };
@@ -265,8 +269,15 @@ cudaError_t launch_project(const float *x, int n, int D, const float *eig, float
 
 cudaError_t launch_pack_codes(const uint16_t *codes, int64_t n, int64_t row0, const ScanLayout &lay, uint4 *packed,
                               cudaStream_t st);
+// Unpacks the ORIGINAL rows [row0, row0+n): storage rows [srow_lo, srow_hi) are visited and row s goes to
+// codes[rowid[s] - row0] when that is in range (rowid == NULL: identity).
 cudaError_t launch_unpack_codes(const uint4 *packed, int64_t row0, int64_t n, const ScanLayout &lay, uint16_t *codes,
-                                cudaStream_t st);
+                                const uint32_t *rowid, int64_t srow_lo, int64_t srow_hi, cudaStream_t st);
+// conflict-aware row order (layout.cu)
+cudaError_t launch_layout(uint4 *codes, int64_t row_lo, int64_t n_rows, const ScanLayout &lay, uint32_t *rowid, uint16_t *src,
+                          uint4 *scratch, int scratch_ctas, bool restore, cudaStream_t st);
+size_t layout_scratch_bytes(int W, int ctas);
+cudaError_t launch_iota_u32(uint32_t *p, int64_t lo, int64_t hi, cudaStream_t st);
 cudaError_t launch_encode(const float *x_proj, int64_t n, const float *centroids, const LutPlan &plan,
                           uint16_t *codes, cudaStream_t st);
 cudaError_t launch_synth_codes(uint16_t *codes, int64_t n, int64_t global_row0, int M, const int32_t *bits,

@@ -39,10 +39,13 @@ __global__ void pack_codes_kernel(const uint16_t *__restrict__ codes, int64_t n,
 }
 
 __global__ void unpack_codes_kernel(const uint4 *__restrict__ packed, int64_t row0, int64_t n,
-                                    const __grid_constant__ ScanLayout lay, uint16_t *__restrict__ codes) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int64_t row = row0 + i;
+                                    const __grid_constant__ ScanLayout lay, uint16_t *__restrict__ codes,
+                                    const uint32_t *__restrict__ rowid, int64_t srow_lo, int64_t srow_hi) {
+  const int64_t row = srow_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // storage row
+  if (row >= srow_hi) return;
+  const int64_t orig = rowid ? (int64_t)rowid[row] : row;
+  if (orig < row0 || orig >= row0 + n) return;
+  const int64_t i = orig - row0;
   const int64_t tile = row >> 5;
   const int lane = (int)(row & 31);
   uint32_t wd[kMaxRowWords + 1];
@@ -71,16 +74,17 @@ cudaError_t launch_pack_codes(const uint16_t *codes, int64_t n, int64_t row0, co
 }
 
 cudaError_t launch_unpack_codes(const uint4 *packed, int64_t row0, int64_t n, const ScanLayout &lay, uint16_t *codes,
-                                cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
+                                const uint32_t *rowid, int64_t srow_lo, int64_t srow_hi, cudaStream_t st) {
+  if (n <= 0 || srow_hi <= srow_lo) return cudaSuccess;
   const int threads = 256;
-  unpack_codes_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(packed, row0, n, lay, codes);
+  unpack_codes_kernel<<<(unsigned)((srow_hi - srow_lo + threads - 1) / threads), threads, 0, st>>>(packed, row0, n, lay, codes, rowid,
+                                                                                              srow_lo, srow_hi);
   return cudaGetLastError();
 }
 
 // ---- synthetic codes ---------------------------------------------------------------------
 // u = splitmix64(seed ^ (row * G1 + s * G2)) >> 40, scaled to [0,1); code = first c with
-// cdf[c] > u (uniform when cdf == NULL).  Restated in numpy by vaq_b200/synth_codes.py.
+// cdf[c] > u (uniform when cdf == NULL).  Restated in numpy by vaq_b200/synth.py.
 __host__ __device__ inline uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
   x ^= x >> 27; x *= 0x94D049BB133111EBull;

@@ -129,6 +129,11 @@ struct vaqgpu_index {
   bool timed = false;
   int32_t cfg[12] = {};
 
+  // conflict-aware row order (layout.cu): d_rowid[storage row] = original row; rows [0, opt_n) are re-ordered
+  uint32_t *d_rowid = nullptr;
+  int64_t rowid_cap = 0, rowid_n = 0, opt_n = 0;
+  float layout_ms = 0.f;
+
   // cross-shard bound exchange (vaqgpu_bounds_*): two halves of bounds_cap entries, used alternately by
   // successive searches; the half the NEXT search will use is reset while this one runs
   uint32_t *d_bounds = nullptr;
@@ -136,7 +141,7 @@ struct vaqgpu_index {
   PeerBounds peers{};
   std::vector<void *> ipc_opened;
 
-  DevBuf w_dbg, w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
+  DevBuf w_lsrc, w_lscratch, w_dbg, w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
 };
 
 struct hamgpu_index {
@@ -325,6 +330,74 @@ int tune_knob(const char *name, int dflt) {
   return dflt;
 }
 
+// ---- conflict-aware row order ---------------------------------------------------------------------------------
+// Row ids exist as soon as any window was re-ordered; from then on they are kept valid for every row (new rows enter
+// at their own index) because every scan kernel forms its keys through them.
+int ensure_rowid(vaqgpu_index *h, cudaStream_t st) {
+  if (!h->d_rowid) return VAQGPU_OK;
+  if (h->rowid_cap < h->n_rows) {
+    uint32_t *nw = nullptr;
+    const int64_t cap = std::max(h->cap_rows, h->n_rows);
+    CU(cudaMalloc(&nw, (size_t)cap * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(nw, h->d_rowid, (size_t)h->rowid_n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(h->d_rowid);
+    h->d_rowid = nw; h->rowid_cap = cap;
+  }
+  if (h->rowid_n < h->n_rows) {
+    CU(launch_iota_u32(h->d_rowid, h->rowid_n, h->n_rows, st));
+    h->rowid_n = h->n_rows;
+  }
+  return VAQGPU_OK;
+}
+
+// Re-orders the windows that hold rows added since the last call (the filter kernels call this before scanning).
+// Skipped while TI clusters are set: their row ranges are defined on the arrival order.
+int ensure_layout(vaqgpu_index *h, cudaStream_t st) {
+  if (h->C > 0 || h->n_rows <= h->opt_n || tune_knob("layout", 1) == 0) return ensure_rowid(h, st);
+  if (!h->d_rowid) {
+    const int64_t cap = std::max(h->cap_rows, h->n_rows);
+    CU(cudaMalloc(&h->d_rowid, (size_t)cap * sizeof(uint32_t)));
+    h->rowid_cap = cap; h->rowid_n = 0;
+  }
+  int rc = ensure_rowid(h, st);
+  if (rc) return rc;
+  const int64_t row_lo = (h->opt_n / kLayoutWin) * kLayoutWin;          // a partially filled window is planned again
+  const int64_t n_windows = (h->n_rows - row_lo + kLayoutWin - 1) / kLayoutWin;
+  const int ctas = (int)std::min<int64_t>(n_windows, 2 * h->num_sms);
+  CU(h->w_lsrc.ensure((size_t)(h->n_rows - row_lo) * sizeof(uint16_t)));
+  CU(h->w_lscratch.ensure(layout_scratch_bytes(h->lay.W, ctas)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, st));
+  CU(launch_layout(h->d_codes, row_lo, h->n_rows, h->lay, h->d_rowid, (uint16_t *)h->w_lsrc.p, (uint4 *)h->w_lscratch.p, ctas, false, st));
+  CU(cudaEventRecord(e1, st));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  h->layout_ms += ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  h->w_lscratch.release();
+  h->opt_n = h->n_rows;
+  return VAQGPU_OK;
+}
+
+// Back to the arrival order (TI cluster ranges are defined on it).
+int restore_layout(vaqgpu_index *h, cudaStream_t st) {
+  if (!h->d_rowid || h->opt_n == 0) return VAQGPU_OK;
+  int rc = ensure_rowid(h, st);
+  if (rc) return rc;
+  const int64_t n_windows = (h->opt_n + kLayoutWin - 1) / kLayoutWin;
+  const int ctas = (int)std::min<int64_t>(n_windows, 2 * h->num_sms);
+  CU(h->w_lsrc.ensure((size_t)h->opt_n * sizeof(uint16_t)));
+  CU(h->w_lscratch.ensure(layout_scratch_bytes(h->lay.W, ctas)));
+  CU(launch_layout(h->d_codes, 0, h->opt_n, h->lay, h->d_rowid, (uint16_t *)h->w_lsrc.p, (uint4 *)h->w_lscratch.p, ctas, true, st));
+  CU(cudaStreamSynchronize(st));
+  h->w_lscratch.release();
+  h->opt_n = 0;
+  return VAQGPU_OK;
+}
+
 // The whole device-side search; exactly one of (d_labels,d_dists) / d_keys is the output.
 //
 // Scan kernel selection (the reference dispatches TI -> EA -> HEAP, VAQ.cpp:799-840):
@@ -347,6 +420,10 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   const bool filter = !ti && !(flags & VAQGPU_SCAN_V1) && h->n_rows > 0;
   const bool want_sqrt = (flags & VAQGPU_SQRT) != 0;
   int launches = 0;
+  {
+    int rc = filter ? ensure_layout(h, st) : ensure_rowid(h, st);
+    if (rc) return rc;
+  }
 
   if (record) CU(cudaEventRecord(h->ev[0], st));
   const float *d_qproj = d_queries;
@@ -432,6 +509,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.peers = peers;
       for (int i = 0; i < peers.n; i++) a.peers.p[i] += q0;
       a.seed = tune_knob("seed", 1);
+      a.rowid = h->d_rowid;
       a.lay = lay;
       const bool dbg = tune_knob("dbg", 0) != 0;
       const size_t n_cta = (size_t)((qb + T - 1) / T) * n_chunks;
@@ -457,7 +535,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
     h->cfg[0] = threads; h->cfg[1] = (int32_t)n_chunks; h->cfg[2] = res_floats; h->cfg[3] = 0;
     h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
-    h->cfg[8] = T; h->cfg[9] = 3; h->cfg[10] = 0;
+    h->cfg[8] = T; h->cfg[9] = 3; h->cfg[10] = h->opt_n > 0; h->cfg[11] = (int32_t)(h->layout_ms * 1000.f);
     return VAQGPU_OK;
   }
 
@@ -514,6 +592,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.peers = peers;
       for (int i = 0; i < peers.n; i++) a.peers.p[i] += q0;
       a.lay = lay;
+      a.rowid = h->d_rowid;
       a.seed = tune_knob("seed", 1);
       a.tile_lo = 0; a.tile_hi = n_tiles; a.chunk_tiles = (int32_t)chunk_tiles; a.slot_base = 0;
       CU(launch_adc_filter_scan(a, T, threads, smem, st));
@@ -527,7 +606,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
     h->cfg[0] = threads; h->cfg[1] = (int32_t)n_chunks; h->cfg[2] = res_floats; h->cfg[3] = spill_floats;
     h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
-    h->cfg[8] = T; h->cfg[9] = 2; h->cfg[10] = 0;
+    h->cfg[8] = T; h->cfg[9] = 2; h->cfg[10] = h->opt_n > 0; h->cfg[11] = (int32_t)(h->layout_ms * 1000.f);
     return VAQGPU_OK;
   }
 
@@ -580,6 +659,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     a.early_abandon = ea ? 1 : 0;
     a.use_tma = 1;
     a.out_keys = (uint64_t *)h->w_keys.p;
+    a.rowid = h->d_rowid;
     if (ti) { a.ranges = (const int2 *)h->w_ranges.p; a.n_ranges = (const int32_t *)h->w_nranges.p; a.max_ranges = h->C; }
     a.lay = lay;
     CU(launch_adc_scan(a, threads, smem, st));
@@ -594,7 +674,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
   h->cfg[0] = threads; h->cfg[1] = splits; h->cfg[2] = res_floats; h->cfg[3] = spill_floats;
   h->cfg[4] = (int32_t)smem; h->cfg[5] = lay.W; h->cfg[6] = launches; h->cfg[7] = qb_max;
-  h->cfg[8] = 1; h->cfg[9] = 1;
+  h->cfg[8] = 1; h->cfg[9] = 1; h->cfg[10] = h->opt_n > 0; h->cfg[11] = (int32_t)(h->layout_ms * 1000.f);
   return VAQGPU_OK;
 }
 
@@ -688,7 +768,8 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_bounds);
-  for (DevBuf *b : {&h->w_dbg, &h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
+  cudaFree(h->d_rowid);
+  for (DevBuf *b : {&h->w_lsrc, &h->w_lscratch, &h->w_dbg, &h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
                     &h->w_labels, &h->w_dists, &h->w_outkeys, &h->w_cdf, &h->w_x})
     b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -811,12 +892,35 @@ int vaqgpu_get_codes_u16(vaqgpu_t *h, int64_t row0, int64_t n, uint16_t *out) {
   DeviceGuard g(h->device);
   const int64_t chunk = std::min<int64_t>(n, kStageRows);
   CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
+  {
+    int rc = ensure_rowid(h, h->stream);
+    if (rc) return rc;
+  }
   for (int64_t r = 0; r < n; r += chunk) {
     const int64_t c = std::min(chunk, n - r);
-    CU(launch_unpack_codes(h->d_codes, row0 + r, c, h->lay, (uint16_t *)h->w_stage.p, h->stream));
+    // storage rows that can hold the original rows [row0 + r, row0 + r + c): the windows they fall into
+    const int64_t slo = h->d_rowid ? ((row0 + r) / kLayoutWin) * kLayoutWin : row0 + r;
+    const int64_t shi = h->d_rowid ? std::min<int64_t>(h->n_rows, ((row0 + r + c + kLayoutWin - 1) / kLayoutWin) * kLayoutWin) : row0 + r + c;
+    CU(launch_unpack_codes(h->d_codes, row0 + r, c, h->lay, (uint16_t *)h->w_stage.p, h->d_rowid, slo, shi, h->stream));
     CU(cudaMemcpyAsync(out + (size_t)r * h->M, h->w_stage.p, (size_t)c * h->M * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
+  return VAQGPU_OK;
+}
+
+int vaqgpu_get_row_order(vaqgpu_t *h, int64_t srow0, int64_t n, uint32_t *out) {
+  if (!h || (!out && n > 0)) return fail(VAQGPU_EINVAL, "handle/out is NULL");
+  if (srow0 < 0 || n < 0 || srow0 + n > h->n_rows) return fail(VAQGPU_EINVAL, "rows [%lld,%lld) outside [0,%lld)", (long long)srow0, (long long)(srow0 + n), (long long)h->n_rows);
+  if (n == 0) return VAQGPU_OK;
+  if (!h->d_rowid) {
+    for (int64_t i = 0; i < n; i++) out[i] = (uint32_t)(srow0 + i);
+    return VAQGPU_OK;
+  }
+  DeviceGuard g(h->device);
+  int rc = ensure_rowid(h, h->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, h->d_rowid + srow0, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return VAQGPU_OK;
 }
 
@@ -888,6 +992,10 @@ int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t s
       return fail(VAQGPU_EINVAL, "cluster %d range [%lld,+%lld) outside the index (%lld rows)", c, (long long)start[c], (long long)size[c], (long long)h->n_rows);
   DeviceGuard g(h->device);
   clear_clusters(h);
+  {
+    int rc = restore_layout(h, h->stream);        // cluster ranges are row ranges of the arrival order
+    if (rc) return rc;
+  }
   auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, bytes);
     return e != cudaSuccess ? e : cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);

@@ -112,6 +112,13 @@ class VAQIndex:
         check(self.lib.vaqgpu_get_codes_u16(self.h, int(row0), int(n), _vp(out)))
         return out
 
+    def get_row_order(self, srow0: int = 0, n: int | None = None) -> np.ndarray:
+        """original index of the rows stored at positions [srow0, srow0+n) (diagnostics; see csrc/layout.cu)"""
+        n = self.num_rows - srow0 if n is None else n
+        out = np.empty(n, np.uint32)
+        check(self.lib.vaqgpu_get_row_order(self.h, int(srow0), int(n), _vp(out)))
+        return out
+
     # -- query path
     def build_lut(self, q_proj) -> np.ndarray:
         q = _c(q_proj, np.float32).reshape(-1, self.D)
@@ -194,7 +201,7 @@ class VAQIndex:
         cfg = (C.c_int32 * 12)()
         check(self.lib.vaqgpu_last_config(self.h, cfg))
         keys = ["threads", "row_chunks", "smem_lut_floats", "spill_lut_floats", "smem_bytes", "row_words", "launches",
-                "queries_per_launch", "queries_per_cta", "scan_kernel"]
+                "queries_per_launch", "queries_per_cta", "scan_kernel", "conflict_aware_layout", "layout_us"]
         return dict(zip(keys, list(cfg)))
 
 
