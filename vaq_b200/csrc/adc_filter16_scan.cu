@@ -93,7 +93,9 @@ __device__ __forceinline__ void atomic_min_half(uint32_t *w, int hi, uint32_t hb
 // TPI 2: 16 warps x two rows per lane — the same rows in flight per SM, but the two independent gather chains of a
 // lane hide the shared-memory latency by instruction-level parallelism, the per-iteration work (bounds, loop, prefetch
 // addressing) is shared by two tiles, and 128 registers per thread keep the stage-1 program out of the loop.
-template <int W, bool FAST1, int TPI>
+// B1 > 0: the four leading fields all have width B1 (e.g. 9,9,9,9 of the 256-bit SIFT models) and their tables are
+// the first four, back to back, in shared memory: shifts, masks and table offsets of stage 1 are immediates.
+template <int W, bool FAST1, int TPI, int B1>
 __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_kernel(const __grid_constant__ AdcFilter16Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -171,6 +173,8 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   }
   const bool two_level = M > 8;
   const int F2 = two_level ? 8 : M;
+  // fields [0, F2) end inside the row's first 128-bit word (the field after them starts at or below bit 128)
+  const bool l1_one_word = F2 < M ? ((int)a.lay.fword[F2] * 32 + (int)(a.lay.fmeta[F2] & 31u) <= 128) : (W == 1);
 
   uint32_t *q1 = queues + (size_t)warp * (q1_cap(TPI) + 2 * kQCap);
   uint32_t *q2 = q1 + q1_cap(TPI);
@@ -339,7 +343,11 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
           for (int i1 = 0; i1 < 4; i1++) {
             if (FAST1 || i1 < G1) {
               uint4 v;
-              if constexpr (FAST1) {
+              if constexpr (B1 > 0) {
+                constexpr uint32_t MK = ((1u << B1) - 1u) << 4;
+                const uint32_t c16 = (i1 == 0 ? (w0.x << 4) : __funnelshift_r(w0.x, w0.y, (uint32_t)(i1 * B1 - 4))) & MK;
+                v = lds128(s_base + (uint32_t)i1 * (16u << B1) + c16);
+              } else if constexpr (FAST1) {
                 // field 0 starts at bit 0 (pair 0 : w0.x), the others at bit >= 4 inside word 0 (pair w0.x : w0.y)
                 const uint32_t c16 = (i1 == 0 ? __funnelshift_r(0u, w0.x, s1_sh[0]) : __funnelshift_r(w0.x, w0.y, s1_sh[i1])) & s1_mask[i1];
                 v = lds128(s1_addr[i1] + c16);
@@ -394,11 +402,14 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
       if constexpr (W <= 2) {
         const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(rp));
         wd[0] = v0.x; wd[1] = v0.y; wd[2] = v0.z; wd[3] = v0.w;
+        wd[4] = wd[5] = wd[6] = wd[7] = 0u;
         if constexpr (W == 2) {
-          const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(rp) + kTileRows);
-          wd[4] = v1.x; wd[5] = v1.y; wd[6] = v1.z; wd[7] = v1.w;
-        } else {
-          wd[4] = wd[5] = wd[6] = wd[7] = 0u;
+          // level 1 only walks the leading fields: when they end inside the first 128-bit word, the second one
+          // (32 more L1 wavefronts for the warp — every lane has its own row) is not fetched
+          if (!(level == 1 && l1_one_word)) {
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(rp) + kTileRows);
+            wd[4] = v1.x; wd[5] = v1.y; wd[6] = v1.z; wd[7] = v1.w;
+          }
         }
       }
       auto selw = [&](int i) -> uint32_t {
@@ -430,11 +441,31 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
         const int fe = level == 1 ? F2 : M;
         __half2 acc[4];
         acc[0] = acc[1] = acc[2] = acc[3] = as_h2(0u);
-        for (int f = 0; f < fe; f++) {
-          const uint32_t code = field_code(f);
-          const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
-          acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
-          acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+        if constexpr (W <= 2) {
+          // walk the row word by word (compile-time register indices), the fields that start in a word in an inner loop
+          int f = 0;
+#pragma unroll
+          for (int w = 0; w < 4 * W; w++) {
+            if (f < fe) {
+              const int few = min(fe, (int)a.lay.fbeg[w + 1]);
+              const uint32_t wlo = wd[w], whi = (w + 1 < 8) ? wd[w + 1] : 0u;
+#pragma unroll 1
+              for (; f < few; f++) {          // 3-4 fields per word at the usual widths: not worth unrolling (code size)
+                const uint32_t meta = a.lay.fmeta[f];
+                const uint32_t code = __funnelshift_r(wlo, whi, meta & 31u) & (meta >> 16);
+                const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
+                acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
+                acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+              }
+            }
+          }
+        } else {
+          for (int f = 0; f < fe; f++) {
+            const uint32_t code = field_code(f);
+            const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
+            acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
+            acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+          }
         }
         mask &= ~dead_mask(acc, s_thr_h + level * 16);
         const unsigned m = __ballot_sync(0xffffffffu, mask != 0);
@@ -528,24 +559,34 @@ size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads) {
   return b;
 }
 
-template <int W, bool FAST1, int TPI>
-static cudaError_t launch16_wft(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
+template <int W, bool FAST1, int TPI, int B1>
+static cudaError_t launch16_wftb(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
   static SmemOptIn optin;
   {
-    cudaError_t e = optin.ensure(adc_filter16_scan_kernel<W, FAST1, TPI>, smem_bytes);
+    cudaError_t e = optin.ensure(adc_filter16_scan_kernel<W, FAST1, TPI, B1>, smem_bytes);
     if (e != cudaSuccess) return e;
   }
   const int64_t nt = a.tile_hi - a.tile_lo;
   if (nt <= 0) return cudaSuccess;
   dim3 grid((unsigned)((a.nq + T8 - 1) / T8), (unsigned)((nt + a.chunk_tiles - 1) / a.chunk_tiles));
-  adc_filter16_scan_kernel<W, FAST1, TPI><<<grid, threads, smem_bytes, st>>>(a);
+  adc_filter16_scan_kernel<W, FAST1, TPI, B1><<<grid, threads, smem_bytes, st>>>(a);
   return cudaGetLastError();
 }
 
 // threads <= 512: two tiles per warp and iteration (TPI 2); more threads: one
 template <int W, bool FAST1>
-static cudaError_t launch16_wf(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
-  return threads <= 512 ? launch16_wft<W, FAST1, 2>(a, threads, smem_bytes, st) : launch16_wft<W, FAST1, 1>(a, threads, smem_bytes, st);
+static cudaError_t launch16_wf(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st, int b1) {
+  if (threads <= 512) return launch16_wftb<W, FAST1, 2, 0>(a, threads, smem_bytes, st);
+  if constexpr (FAST1 && W <= 2) {
+    switch (b1) {          // uniform leading widths met in practice (budget / subspaces around 8 bits)
+      case 7: return launch16_wftb<W, true, 1, 7>(a, threads, smem_bytes, st);
+      case 8: return launch16_wftb<W, true, 1, 8>(a, threads, smem_bytes, st);
+      case 9: return launch16_wftb<W, true, 1, 9>(a, threads, smem_bytes, st);
+      case 10: return launch16_wftb<W, true, 1, 10>(a, threads, smem_bytes, st);
+      default: break;
+    }
+  }
+  return launch16_wftb<W, FAST1, 1, 0>(a, threads, smem_bytes, st);
 }
 
 template <int W>
@@ -554,7 +595,15 @@ static cudaError_t launch16_w(const AdcFilter16Args &a, int threads, size_t smem
   bool fast1 = a.lay.M >= 4;
   for (int f = 0; f < 4 && fast1; f++) fast1 = a.lay.fword[f] == 0;
   if (fast1) fast1 = (a.lay.fmeta[1] & 31u) >= 4u;
-  return fast1 ? launch16_wf<W, true>(a, threads, smem_bytes, st) : launch16_wf<W, false>(a, threads, smem_bytes, st);
+  // B1: ... all of the same width, their tables first and back to back
+  int b1 = 0;
+  if (fast1) {
+    const uint32_t mask = a.lay.fmeta[0] >> 16;
+    b1 = __builtin_popcount(mask);
+    for (int f = 0; f < 4; f++)
+      if ((a.lay.fmeta[f] >> 16) != mask || a.lay.foff[f] != (uint32_t)f << b1) b1 = 0;
+  }
+  return fast1 ? launch16_wf<W, true>(a, threads, smem_bytes, st, b1) : launch16_wf<W, false>(a, threads, smem_bytes, st, 0);
 }
 
 cudaError_t launch_adc_filter16_scan(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {

@@ -469,9 +469,10 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     if (adc_filter16_smem_bytes(plan.row_stride, k, 1024) > kSmemCap) filter16 = false;
   }
   if (filter16) {
-    // 32 warps per CTA on long chunks; 16 on short ones (every warp starts by scoring rows exactly until the
-    // CTA's bounds settle, so on a short chunk fewer warps waste less before the first useful bound)
-    const int T = 8, threads = tune_knob("threads", h->n_rows >= 400000 ? 1024 : 512);
+    // 32 warps x one row per lane (measured faster than 16 warps x two rows per lane at every chunk length: the scan
+    // is bound by shared-memory wavefronts and issue slots, which more resident warps fill better; the 512-thread
+    // variant stays selectable with VAQGPU_TUNE=threads=512)
+    const int T = 8, threads = tune_knob("threads", 1024);
     const size_t smem = adc_filter16_smem_bytes(plan.row_stride, k, threads);
     const int nwarps = threads / 32;
     const size_t bytes_per_q = (size_t)plan.row_stride * 4;
