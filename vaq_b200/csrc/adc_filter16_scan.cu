@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int k = a.k;
-  const int qt = blockIdx.x, chunk = blockIdx.y;
+  // grid: query tiles on x, row chunks on y (all tiles sweep a chunk while it is L2-resident); chunks_fast swaps them
+  // so that the chunks of one query tile run concurrently and share their bounds (few queries, development)
+  const int qt = a.chunks_fast ? blockIdx.y : blockIdx.x, chunk = a.chunks_fast ? blockIdx.x : blockIdx.y;
   const int q0 = qt * T8;
 
   const size_t lut_bytes = (size_t)a.lut_stride * T8 * sizeof(__half);       // multiple of 64
@@ -234,33 +236,34 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
           wd[4] = wd[5] = wd[6] = wd[7] = 0u;
         }
       }
-      auto selw = [&](int i) -> uint32_t {
-        const uint32_t s0 = (i & 1) ? wd[1] : wd[0], s1 = (i & 1) ? wd[3] : wd[2];
-        const uint32_t s2 = (i & 1) ? wd[5] : wd[4], s3 = (i & 1) ? wd[7] : wd[6];
-        const uint32_t t0 = (i & 2) ? s1 : s0, t1 = (i & 2) ? s3 : s2;
-        return (i & 8) ? 0u : ((i & 4) ? t1 : t0);
-      };
-      int widx = -2;
-      uint32_t lo = 0u, hi = 0u;
       __half2 acc[4];
       acc[0] = acc[1] = acc[2] = acc[3] = as_h2(0u);
-      for (int f = 0; f < M; f++) {
-        const uint32_t meta = a.lay.fmeta[f];
-        if constexpr (W <= 2) {
-          const int fw = a.lay.fword[f];
-          if (fw != widx) {
-            lo = (fw == widx + 1) ? hi : selw(fw);
-            hi = selw(fw + 1);
-            widx = fw;
+      if constexpr (W <= 2) {
+        // word by word (compile-time register indices), the fields that start in a word in an inner loop
+        int f = 0;
+#pragma unroll
+        for (int w = 0; w < 4 * W; w++) {
+          const int few = (int)a.lay.fbeg[w + 1];
+          const uint32_t wlo = wd[w], whi = (w + 1 < 8) ? wd[w + 1] : 0u;
+#pragma unroll 1
+          for (; f < few; f++) {
+            const uint32_t meta = a.lay.fmeta[f];
+            const uint32_t code = __funnelshift_r(wlo, whi, meta & 31u) & (meta >> 16);
+            const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
+            acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
+            acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
           }
-        } else {
-          lo = __ldg(rp + a.lay.fw_lo[f]);
-          hi = __ldg(rp + a.lay.fw_hi[f]);
         }
-        const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
-        const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
-        acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
-        acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+      } else {
+        for (int f = 0; f < M; f++) {
+          const uint32_t meta = a.lay.fmeta[f];
+          const uint32_t lo = __ldg(rp + a.lay.fw_lo[f]);
+          const uint32_t hi = __ldg(rp + a.lay.fw_hi[f]);
+          const uint32_t code = __funnelshift_r(lo, hi, meta & 31u) & (meta >> 16);
+          const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
+          acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
+          acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+        }
       }
 #pragma unroll
       for (int i = 0; i < 4; i++) best[i] = __hmin2(best[i], acc[i]);
@@ -280,14 +283,15 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
     if (warp < T8 && q0 + warp < a.nq) {
       // warp t: k-th smallest of query t's n minima by bisection over the 15-bit pattern space
       const uint32_t *col = reinterpret_cast<const uint32_t *>(lm + warp * n);
+      uint32_t vals[16];                               // this lane's share of the n <= 1024 minima, two per word
+#pragma unroll
+      for (int i = 0; i < 16; i++) vals[i] = (lane + 32 * i < n / 2) ? col[lane + 32 * i] : 0x7C007C00u;
       uint32_t lo = 0u, hi = 0x7C00u;                // +inf: fewer than k finite values -> no seed
       while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         int cnt = 0;
-        for (int i = lane; i < n / 2; i += 32) {
-          const uint32_t v = col[i];
-          cnt += ((v & 0xFFFFu) <= mid) + ((v >> 16) <= mid);
-        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) cnt += ((vals[i] & 0xFFFFu) <= mid) + ((vals[i] >> 16) <= mid);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (cnt >= k) hi = mid; else lo = mid + 1;
@@ -569,6 +573,7 @@ static cudaError_t launch16_wftb(const AdcFilter16Args &a, int threads, size_t s
   const int64_t nt = a.tile_hi - a.tile_lo;
   if (nt <= 0) return cudaSuccess;
   dim3 grid((unsigned)((a.nq + T8 - 1) / T8), (unsigned)((nt + a.chunk_tiles - 1) / a.chunk_tiles));
+  if (a.chunks_fast) { const unsigned t = grid.x; grid.x = grid.y; grid.y = t; }
   adc_filter16_scan_kernel<W, FAST1, TPI, B1><<<grid, threads, smem_bytes, st>>>(a);
   return cudaGetLastError();
 }

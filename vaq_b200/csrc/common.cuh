@@ -255,6 +255,7 @@ struct AdcFilter16Args {
   PeerBounds peers;          // the same array on the other row shards (n = 0: single shard)
   int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
   const uint32_t *rowid;     // original row index of each storage row (layout.cu), or NULL = identity
+  int32_t chunks_fast;       // grid order: 0 = query tiles fastest (default), 1 = row chunks fastest
   long long *dbg;            // development: per-CTA phase clocks (NULL = off)
   ScanLayout lay;
 };

@@ -77,27 +77,23 @@ __global__ void __launch_bounds__(256, (W <= 2 ? 4 : 2)) ham_scan_kernel(const _
   const int n_tiles = (int)((a.n_rows + kTileRows - 1) >> 5);
   const int g = split * nwarps + warp, gstride = a.splits * nwarps;
   int t = g;
-  // Register ring of PF tiles per warp: with one or two queries per pass the scan is pure streaming and the bytes in
-  // flight per SM (warps x PF x 512 B x W) decide how close it gets to the HBM roofline; with more queries per pass
-  // the popcount work hides the latency and two tiles are enough.
-  constexpr int PF = (QT <= 2 && W <= 2) ? 4 : 2;
-  uint4 buf[PF][W];
+  uint4 cur[W], nxt[W];
   auto load = [&](uint4(&dst)[W], int tile) {
     const uint4 *p = a.codes + ((size_t)tile * W) * kTileRows + lane;
 #pragma unroll
     for (int j = 0; j < W; j++) dst[j] = ldg_stream_u4(p + j * kTileRows);
   };
-#pragma unroll
-  for (int s = 0; s < PF; s++)
-    if (t + s * gstride < n_tiles) load(buf[s], t + s * gstride);
+  if (t < n_tiles) load(cur, t);
   // distance part of each query's running k-th key, kept in registers: the per-row test is one compare;
   // the exact (distance, row) key test and the list update only run for rows that pass it
   uint32_t thr_d[QT];
 #pragma unroll
   for (int qi = 0; qi < QT; qi++) thr_d[qi] = 0xFFFFFFFFu;
   int iter = 0;
-  auto process = [&](const uint4(&cur)[W], int tile) {
-    const int row = tile * kTileRows + lane;
+  for (; t < n_tiles; t += gstride, iter++) {
+    const int tn = t + gstride;
+    if (tn < n_tiles) load(nxt, tn);
+    const int row = t * kTileRows + lane;
     const bool valid = row < a.n_rows;
     if ((iter & 15) == 15) {
       // adopt tighter bounds other warps of the CTA have reached
@@ -105,7 +101,6 @@ __global__ void __launch_bounds__(256, (W <= 2 ? 4 : 2)) ham_scan_kernel(const _
       for (int qi = 0; qi < QT; qi++)
         thr_d[qi] = min(thr_d[qi], (uint32_t)(*reinterpret_cast<volatile uint64_t *>(blk_thr + qi) >> 32));
     }
-    iter++;
 #pragma unroll
     for (int qi = 0; qi < QT; qi++) {
       if (qi < nqt) {
@@ -129,17 +124,8 @@ __global__ void __launch_bounds__(256, (W <= 2 ? 4 : 2)) ham_scan_kernel(const _
         }
       }
     }
-  };
-  while (t < n_tiles) {
 #pragma unroll
-    for (int s = 0; s < PF; s++) {
-      if (t < n_tiles) {
-        process(buf[s], t);
-        const int tn = t + PF * gstride;
-        if (tn < n_tiles) load(buf[s], tn);
-        t += gstride;
-      }
-    }
+    for (int j = 0; j < W; j++) cur[j] = nxt[j];
   }
 
   __syncthreads();

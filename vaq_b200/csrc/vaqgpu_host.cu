@@ -277,27 +277,26 @@ size_t scan_smem_bytes(int smem_lut_floats, int k, int threads) {
   return b;
 }
 
-// Row chunks per query tile for the filter kernels (grid = query tiles x chunks, one CTA per SM): enough CTAs to
-// fill the machine ~3x when there are few query tiles, every warp left with >= 16 tiles, chunks of at most 1M rows
-// so that all query tiles sweep a chunk while it is L2-resident — and, when the grid is only a few waves long, the
-// count in [c, 4c/3] whose last wave is fullest (CTAs come in multiples of the SM count).
+// Row chunks per query tile for the filter kernels (grid = query tiles x chunks, one CTA per SM).  Chunks hold at
+// most 1M rows (all query tiles sweep a chunk while it is L2-resident) and leave every warp >= 16 tiles.  Within
+// those limits the count minimises a simple cost model: CTAs run in waves of one per SM, and a CTA costs a fixed
+// ~45 us (table staging, bound seeding, queue drain) plus ~0.9 ns per row (measured, SIFT1M shape) — so a handful of
+// queries gets exactly one wave of long CTAs, many query tiles get as few chunks as the L2 rule allows, and a grid
+// that is only a few waves long avoids a nearly empty last wave.
 int64_t choose_chunks(int64_t n_tiles, int qtiles, int nwarps, int num_sms) {
-  const int64_t target = (int64_t)num_sms * 3;
-  const int64_t cap = std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16));
-  int64_t c = std::max<int64_t>(1, (target + qtiles - 1) / qtiles);
-  c = std::min(c, cap);
-  c = std::max<int64_t>(c, (n_tiles + 32767) / 32768);
-  if (c * qtiles <= 16ll * num_sms && c > 1) {
-    double best = 0.0;
-    int64_t pick = c;
-    for (int64_t t = c; t <= std::min(cap, c + c / 3 + 1); t++) {
-      const int64_t ctas = t * qtiles, waves = (ctas + num_sms - 1) / num_sms;
-      const double eff = (double)ctas / (double)(waves * num_sms);
-      if (eff > best + 1e-9) { best = eff; pick = t; }
-    }
-    c = pick;
+  const int64_t c_max = std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16));
+  const int64_t c_min = std::min(c_max, std::max<int64_t>(1, (n_tiles + 32767) / 32768));
+  const double t_fixed = 45.0, t_row = 0.0009;         // microseconds
+  double best = 0.0;
+  int64_t pick = c_min;
+  const int64_t c_hi = std::min<int64_t>(c_max, std::max<int64_t>(c_min * 2, (4ll * num_sms + qtiles - 1) / qtiles));
+  for (int64_t c = c_min; c <= c_hi; c++) {
+    const int64_t ctas = c * qtiles, waves = (ctas + num_sms - 1) / num_sms;
+    const double rows = 32.0 * (double)((n_tiles + c - 1) / c);
+    const double cost = (double)waves * (t_fixed + rows * t_row);
+    if (c == c_min || cost < best * 0.999) { best = cost; pick = c; }
   }
-  return c;
+  return pick;
 }
 
 int ensure_stream(cudaStream_t *st, cudaEvent_t *ev, int nev) {
@@ -511,6 +510,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       for (int i = 0; i < peers.n; i++) a.peers.p[i] += q0;
       a.seed = tune_knob("seed", 1);
       a.rowid = h->d_rowid;
+      a.chunks_fast = tune_knob("chunks_fast", 0);
       a.lay = lay;
       const bool dbg = tune_knob("dbg", 0) != 0;
       const size_t n_cta = (size_t)((qb + T - 1) / T) * n_chunks;
