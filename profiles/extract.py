@@ -35,6 +35,12 @@ if len(sys.argv) > 5:
         return float(v) * m
     tj_path = HERE / "ncu_traffic.json"
     tj = json.loads(tj_path.read_text()) if tj_path.exists() else {}
-    tj[sys.argv[3]] = {"workload": sys.argv[4], "n_gpus": int(sys.argv[5]), "dram_bytes_read": num("dram__bytes_read.sum"),
-                       "dram_bytes_write": num("dram__bytes_write.sum"), "source": f"profiles/{tag}_summary.json"}
+    ent = {"workload": sys.argv[4], "n_gpus": int(sys.argv[5]), "dram_bytes_read": num("dram__bytes_read.sum"),
+           "dram_bytes_write": num("dram__bytes_write.sum"), "gpu_time": out.get("gpu__time_duration.sum"),
+           "source": f"profiles/{tag}_summary.json"}
+    cur = tj.get(sys.argv[3], [])
+    if isinstance(cur, dict):
+        cur = [cur]
+    cur = [e for e in cur if not (e.get("workload") == ent["workload"] and e.get("n_gpus") == ent["n_gpus"])] + [ent]
+    tj[sys.argv[3]] = cur
     tj_path.write_text(json.dumps(tj, indent=1))

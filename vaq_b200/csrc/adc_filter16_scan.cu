@@ -217,8 +217,14 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   // is an UPPER bound of the row's distance (M <= 64: 1.001 * 1.032 < 1.0625).  The lanes' sample rows are
   // distinct, so the k-th smallest of the per-lane minima is the upper bound of k distinct rows' distances, hence
   // bounds the k-th best distance of the chunk.
-  const int spl = (int)min(4u, rows_here / (blockDim.x * 4u));      // sample rows per lane: at most a quarter of the chunk
-  if (a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64) {
+  // Sample rows per lane: at most a quarter of the chunk, and about one per 128 K rows (1 .. 4) — scoring a sample row
+  // costs as much as the whole lower-bound walk of a survivor, so a short chunk takes a smaller sample (32 us for 4096
+  // rows is a tenth of a 125 K-row chunk's scan).  A CTA whose queries all arrive with a bound (later row chunks of a
+  // query tile, or bounds already published by other shards) skips the seeding altogether.
+  const int spl = (int)min(min(4u, max(1u, rows_here >> 17)), rows_here / (blockDim.x * 4u));
+  int unbounded = 0;
+  if (tid < T8 && q0 + tid < a.nq) unbounded = thr_f[tid] == 0xFFFFFFFFu;
+  if (a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64 && __syncthreads_or(unbounded)) {
     const uint32_t step = rows_here / (blockDim.x * (uint32_t)spl);
     __half2 best[4];
     best[0] = best[1] = best[2] = best[3] = as_h2(0x7C007C00u);        // +inf

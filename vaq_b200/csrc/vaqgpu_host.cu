@@ -287,6 +287,7 @@ int64_t choose_chunks(int64_t n_tiles, int qtiles, int nwarps, int num_sms) {
   const int64_t c_max = std::max<int64_t>(1, n_tiles / ((int64_t)nwarps * 16));
   const int64_t c_min = std::min(c_max, std::max<int64_t>(1, (n_tiles + 32767) / 32768));
   const double t_fixed = 45.0, t_row = 0.0009;         // microseconds
+  if (qtiles >= 2 * num_sms) return c_min;            // many waves either way: no reason to pay the fixed cost twice
   double best = 0.0;
   int64_t pick = c_min;
   const int64_t c_hi = std::min<int64_t>(c_max, std::max<int64_t>(c_min * 2, (4ll * num_sms + qtiles - 1) / qtiles));
