@@ -149,6 +149,10 @@ int vaqgpu_bounds_attach_ptr(vaqgpu_t *h, int32_t n_peers, void *const *peer_ptr
 int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t segdims,
                         const int64_t *start, const int64_t *size, const int32_t *id_map);
 int vaqgpu_set_visit(vaqgpu_t *h, float visit);
+/* Row-sharded TI: a shard's vaqgpu_set_clusters holds the part of each cluster that falls into its rows; the visiting
+ * rule ("continue while fewer than k rows were covered", VAQ.cpp:1555,1616-1618) must count the clusters' sizes in the
+ * whole index.  sizes: [C]. */
+int vaqgpu_set_cluster_rule_sizes(vaqgpu_t *h, const int64_t *sizes);
 
 /* replaces VAQ::refine (VAQ.cpp:849-876): exact squared-L2 re-rank of `refine_num` candidate
  * labels per query against raw vectors.  xtrain: host [n x D0] raw rows (uploaded once and

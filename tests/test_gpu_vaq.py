@@ -535,3 +535,70 @@ def test_layout_restored_for_ti_after_plain_searches(port):
     lab, dis = ix.search(g["Q"], int(g["k"]), TI | EA | SQRT | PROJECTED)
     assert_knn_equiv(lab, dis, g["ti_lab_v25"], g["ti_dis_v25"], what="TI visit 0.25 after layout restore")
     ix.close()
+
+
+# ---- TI / visit on the filter kernel ---------------------------------------------------------------------------------
+
+def ti_visited_sets(Q, clusters, sizes, visit, k):
+    """numpy restatement of the visiting rule (VAQ.cpp:799-827, 1548-1555, 1616-1618): clusters ranked by the sqrt of the
+    sequential fp32 sum of squares over the first segdims dims (ties by index); the nearest floor(C*visit) are visited
+    (all when visit >= 1), and the visit goes on while fewer than k rows were covered (empty clusters cover nothing)."""
+    C, seg = clusters.shape
+    out = []
+    for q in Q:
+        acc = np.zeros(C, np.float32)
+        for j in range(seg):
+            d = (np.float32(q[j]) - clusters[:, j]).astype(np.float32)
+            acc = (acc + (d * d).astype(np.float32)).astype(np.float32)
+        dist = np.sqrt(acc).astype(np.float32)
+        order = np.lexsort((np.arange(C), dist))
+        max_visit = C if visit >= 1.0 else int(np.float32(C) * np.float32(visit))
+        vis, seen, enough = [], 0, False
+        for pos, cl in enumerate(order):
+            if not (pos < max_visit or not enough):
+                break
+            if sizes[cl] == 0:
+                continue
+            vis.append(int(cl)); seen += int(sizes[cl])
+            if seen >= k:
+                enough = True
+        out.append(vis)
+    return out
+
+
+@pytest.mark.parametrize("visit,k", [(1.0, 10), (0.25, 10), (0.05, 10), (0.01, 200)])
+def test_ti_on_filter_kernel_matches_exhaustive_over_visited_clusters(port, visit, k):
+    from vaq_b200.index import EA, PROJECTED, SCAN_V1, SQRT, TI
+    rng = np.random.default_rng(4242)
+    bits = [9, 9, 9, 9, 8, 8, 7, 7, 6, 6, 5, 5]
+    m = random_model(rng, len(bits), 2, bits)
+    n, C, seg = 50000, 300, 8
+    sizes = rng.integers(0, 400, size=C)
+    sizes[[3, 4, 50, 299]] = 0                                   # empty clusters, also the last one
+    sizes[[10, 11, 12]] = [1, 2, 31]                             # tiny ones (several clusters inside one 32-row tile)
+    sizes = (sizes * (n / sizes.sum())).astype(np.int64)
+    sizes[0] += n - sizes.sum()
+    start = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+    codes = random_codes(rng, m, n)
+    codes[1000:1200] = codes[:200]                               # ties
+    id_map = rng.permutation(n).astype(np.int32)
+    clusters = rng.standard_normal((C, seg)).astype(np.float32)
+    Q = rng.standard_normal((37, m.D)).astype(np.float32)
+    ix = make_index(m, codes=codes)
+    ix.set_clusters(clusters, start, sizes, id_map)
+    ix.set_visit(visit)
+    visited = ti_visited_sets(Q, clusters, sizes, visit, k)
+    lut = port.create_lut(m, Q)
+    for extra, kern in ((0, 3), (SCAN_V1, 1)):
+        lab, dis = ix.search(Q, k, TI | EA | SQRT | PROJECTED | extra)
+        assert ix.last_config()["scan_kernel"] == kern
+        for q in range(Q.shape[0]):
+            rows = np.concatenate([np.arange(start[c], start[c] + sizes[c]) for c in visited[q]]) if visited[q] else np.zeros(0, np.int64)
+            d = port.adc_all(m, lut[q], codes[rows])
+            order = np.lexsort((rows, d))[:k]
+            want_lab = np.full(k, -1, np.int32); want_dis = np.full(k, np.finfo(np.float32).max, np.float32)
+            want_lab[:order.size] = id_map[rows[order]]
+            want_dis[:order.size] = np.sqrt(d[order]).astype(np.float32)
+            assert np.array_equal(lab[q], want_lab), f"visit={visit} kernel={kern} query {q}"
+            assert bitwise_equal(dis[q], want_dis)
+    ix.close()

@@ -95,7 +95,9 @@ __device__ __forceinline__ void atomic_min_half(uint32_t *w, int hi, uint32_t hb
 // addressing) is shared by two tiles, and 128 registers per thread keep the stage-1 program out of the loop.
 // B1 > 0: the four leading fields all have width B1 (e.g. 9,9,9,9 of the 256-bit SIFT models) and their tables are
 // the first four, back to back, in shared memory: shifts, masks and table offsets of stage 1 are immediates.
-template <int W, bool FAST1, int TPI, int B1>
+// TI: the query tile only visits some clusters of the (cluster-grouped) matrix: a byte per cluster says which of the
+// tile's queries do; row tiles of unvisited clusters are skipped, the others start with that mask.
+template <int W, bool FAST1, int TPI, int B1, bool TI>
 __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_kernel(const __grid_constant__ AdcFilter16Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   uint64_t *lists = reinterpret_cast<uint64_t *>(locks + 8);                 // [8][k] ascending exact keys
   uint64_t *bar = lists + (size_t)T8 * k;
   uint32_t *queues = reinterpret_cast<uint32_t *>(bar + 1);                  // per warp: q1 | q2 | q3, (row << 8) | query mask
+  uint8_t *smask = reinterpret_cast<uint8_t *>(queues + (size_t)nwarps * (q1_cap(TPI) + 2 * kQCap));      // [C] (TI only)
 
   const unsigned char *g16 = reinterpret_cast<const unsigned char *>(a.lut16) + (size_t)qt * lut_bytes;
   const float *g32 = a.lut32 + (size_t)qt * a.lut_stride * T8;
@@ -130,9 +133,14 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (dbg && tid == 0) dbg[0] = clock64();
   for (int i = tid; i < T8 * k; i += blockDim.x) lists[i] = kEmptyKey;
+  // index of a tile slot in the per-query bound arrays: the query's position in the caller's batch (TI searches run
+  // the queries in tile order — a permutation that may differ between shards, while the bound arrays are exchanged)
+  auto bound_index = [&](int t) -> int {
+    const int q = min(q0 + t, a.nq - 1);
+    if constexpr (TI) return a.qmap[q]; else return q;
+  };
   if (tid < T8) {
-    const int q = min(q0 + tid, a.nq - 1);
-    const uint32_t g = a.thr_global[q];
+    const uint32_t g = a.thr_global[bound_index(tid)];
     const float sc = a.scale[q0 + tid];
     scale_s[tid] = sc;
     thr_f[tid] = g;
@@ -153,7 +161,12 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
       tma_bulk_g2s(smem_raw + off, g16 + off, n, bar);
     }
   }
+  if constexpr (TI) {
+    const uint8_t *gm = a.tmask + (size_t)qt * a.C;
+    for (int c = tid; c < a.C; c += blockDim.x) smask[c] = gm[c];
+  }
   mbar_wait(bar, 0);
+  if constexpr (TI) __syncthreads();
   if (dbg && tid == 0) dbg[1] = clock64();
 
   // stage-1 program: the first group (<= 4 fields, <= 60 bits, i.e. inside 32-bit words 0..2).  The code is
@@ -217,14 +230,13 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   // is an UPPER bound of the row's distance (M <= 64: 1.001 * 1.032 < 1.0625).  The lanes' sample rows are
   // distinct, so the k-th smallest of the per-lane minima is the upper bound of k distinct rows' distances, hence
   // bounds the k-th best distance of the chunk.
-  // Sample rows per lane: at most a quarter of the chunk, and about one per 128 K rows (1 .. 4) — scoring a sample row
-  // costs as much as the whole lower-bound walk of a survivor, so a short chunk takes a smaller sample (32 us for 4096
-  // rows is a tenth of a 125 K-row chunk's scan).  A CTA whose queries all arrive with a bound (later row chunks of a
-  // query tile, or bounds already published by other shards) skips the seeding altogether.
-  const int spl = (int)min(min(4u, max(1u, rows_here >> 17)), rows_here / (blockDim.x * 4u));
+  // Sample rows per lane: at most a quarter of the chunk.  (A smaller sample on short chunks was measured slower: the
+  // looser seed costs more in the first passes than the sampling saves.)  A CTA whose queries all arrive with a bound
+  // (later row chunks of a query tile, or bounds already published by other shards) skips the seeding altogether.
+  const int spl = (int)min(4u, rows_here / (blockDim.x * 4u));
   int unbounded = 0;
   if (tid < T8 && q0 + tid < a.nq) unbounded = thr_f[tid] == 0xFFFFFFFFu;
-  if (a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64 && __syncthreads_or(unbounded)) {
+  if (!TI && a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64 && __syncthreads_or(unbounded)) {
     const uint32_t step = rows_here / (blockDim.x * (uint32_t)spl);
     __half2 best[4];
     best[0] = best[1] = best[2] = best[3] = as_h2(0x7C007C00u);        // +inf
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
         const float ub = (x * (1.f + 1.f / 16.f) + (float)M * 5.9604645e-8f) / scale_s[warp] * (1.f + 1e-6f) + 1e-30f;
         if (ub < 3.0e38f) {
           publish_bound(warp, __float_as_uint(ub));
-          publish_global_bound(a.thr_global, a.peers, q0 + warp, __float_as_uint(ub));      // a valid bound for every chunk and shard
+          publish_global_bound(a.thr_global, a.peers, bound_index(warp), __float_as_uint(ub));      // a valid bound for every chunk and shard
         }
       }
     }
@@ -338,15 +350,25 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
 #pragma unroll
         for (int u = 0; u < TPI; u++)
           if (it + (2 * TPI + u) * nwarps < n_it) nxt[u] = ldg_stream_u4(pnext + u * pstep);
+        if (a.l2_prefetch > 0 && (lane & 7) == 0 && it + (2 * TPI + a.l2_prefetch) * nwarps < n_it)
+          prefetch_l2(pnext + (size_t)a.l2_prefetch * pstep);      // first words of a later tile, one 128-byte line per 8 lanes
         if (((++refresh) & (TPI == 2 ? 15 : 31)) == 0 && lane < T8 && q0 + lane < a.nq) {
           // pick up bounds published by other row chunks of this query tile (and, row-sharded, by other GPUs)
-          const uint32_t g = *reinterpret_cast<volatile uint32_t *>(a.thr_global + q0 + lane);
+          const uint32_t g = *reinterpret_cast<volatile uint32_t *>(a.thr_global + bound_index(lane));
           if (g < *reinterpret_cast<volatile uint32_t *>(thr_f + lane)) publish_bound(lane, g);
         }
         const uint4 th = lds128_volatile(s_thr_h);      // the eight stage-1 bounds, two per word like the accumulators
         unsigned sb[TPI];
 #pragma unroll
         for (int u = 0; u < TPI; u++) {
+          unsigned cm = 0xFFu;          // queries of the tile that visit this row's cluster
+          if constexpr (TI) {
+            const int itu = it + u * nwarps;
+            const uint32_t ci = itu < n_it ? (uint32_t)__ldg(a.tile_cl + tile_begin + itu) : 0u;
+            if (ci != 0xFFFFu) cm = smask[ci];
+            else cm = smask[cluster_of_row(a.cl_start, a.C, row_base + ((int64_t)itu << 5) + lane)];
+            if (!__any_sync(0xffffffffu, cm != 0u)) { sb[u] = 0u; continue; }          // nobody visits: no gathers
+          }
           const uint4 w0 = w[u];
           __half2 acc[4];
 #pragma unroll
@@ -373,7 +395,7 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
               }
             }
           }
-          sb[u] = ~dead_mask_th(acc, th) & 0xFFu;
+          sb[u] = ~dead_mask_th(acc, th) & cm;
         }
 #pragma unroll
         for (int u = 0; u < TPI; u++) {
@@ -541,7 +563,7 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
               if (kth != before && kth != kEmptyKey) {
                 const uint32_t bits = (uint32_t)(kth >> 32);
                 publish_bound(tt, bits);
-                publish_global_bound(a.thr_global, a.peers, q0 + tt, bits);
+                publish_global_bound(a.thr_global, a.peers, bound_index(tt), bits);
               }
             }
           }
@@ -561,32 +583,34 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   }
 }
 
-size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads) {
+size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads, int ti_clusters) {
   const int nwarps = threads / 32, tpi = threads <= 512 ? 2 : 1;
   size_t b = (size_t)lut_stride * T8 * 2 + 6 * 32;          // tables + bounds/scales/locks
   b += ((size_t)T8 * k + 1) * sizeof(uint64_t);
   b += (size_t)nwarps * (q1_cap(tpi) + 2 * kQCap) * sizeof(uint32_t);
+  b += ((size_t)ti_clusters + 15) & ~(size_t)15;          // TI: one mask byte per cluster
   return b;
 }
 
-template <int W, bool FAST1, int TPI, int B1>
+template <int W, bool FAST1, int TPI, int B1, bool TI = false>
 static cudaError_t launch16_wftb(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st) {
   static SmemOptIn optin;
   {
-    cudaError_t e = optin.ensure(adc_filter16_scan_kernel<W, FAST1, TPI, B1>, smem_bytes);
+    cudaError_t e = optin.ensure(adc_filter16_scan_kernel<W, FAST1, TPI, B1, TI>, smem_bytes);
     if (e != cudaSuccess) return e;
   }
   const int64_t nt = a.tile_hi - a.tile_lo;
   if (nt <= 0) return cudaSuccess;
   dim3 grid((unsigned)((a.nq + T8 - 1) / T8), (unsigned)((nt + a.chunk_tiles - 1) / a.chunk_tiles));
   if (a.chunks_fast) { const unsigned t = grid.x; grid.x = grid.y; grid.y = t; }
-  adc_filter16_scan_kernel<W, FAST1, TPI, B1><<<grid, threads, smem_bytes, st>>>(a);
+  adc_filter16_scan_kernel<W, FAST1, TPI, B1, TI><<<grid, threads, smem_bytes, st>>>(a);
   return cudaGetLastError();
 }
 
 // threads <= 512: two tiles per warp and iteration (TPI 2); more threads: one
 template <int W, bool FAST1>
 static cudaError_t launch16_wf(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st, int b1) {
+  if (a.tmask) return launch16_wftb<W, FAST1, 1, 0, true>(a, 1024, smem_bytes, st);          // TI / visit
   if (threads <= 512) return launch16_wftb<W, FAST1, 2, 0>(a, threads, smem_bytes, st);
   if constexpr (FAST1 && W <= 2) {
     switch (b1) {          // uniform leading widths met in practice (budget / subspaces around 8 bits)

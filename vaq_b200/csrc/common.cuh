@@ -82,6 +82,9 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p) {
   return r;
 }
 
+// L2 prefetch of the line holding p: hides DRAM latency of a streaming scan several tiles ahead at no register cost
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -140,6 +143,17 @@ __device__ __forceinline__ uint64_t warp_list_insert(volatile uint64_t *list, in
     if (base <= rank) break;   // everything below `rank` is unchanged
   }
   return list[k - 1];
+}
+
+// Cluster of a row of the cluster-grouped matrix: the last cluster whose first row is <= row (starts ascend; an
+// empty cluster shares its start with its successor and is never returned for a real row).
+__device__ __forceinline__ int cluster_of_row(const int64_t *__restrict__ start, int C, int64_t row) {
+  int lo = 0, hi = C;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (start[mid] <= row) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
 }
 
 // count of entries < key in an ascending list (binary search)
@@ -256,10 +270,18 @@ struct AdcFilter16Args {
   int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
   const uint32_t *rowid;     // original row index of each storage row (layout.cu), or NULL = identity
   int32_t chunks_fast;       // grid order: 0 = query tiles fastest (default), 1 = row chunks fastest
+  int32_t l2_prefetch;       // > 0: stage 1 prefetches into L2 this many iterations ahead (code matrix >> L2)
+  // TI / visit (NULL / 0 otherwise): cluster of each 32-row tile (0xFFFF = straddles clusters), first row of each
+  // cluster, and per (query tile, cluster) the 8-bit mask of the tile's queries that visit the cluster
+  const uint16_t *tile_cl;
+  const int64_t *cl_start;
+  const uint8_t *tmask;
+  const int32_t *qmap;       // TI: position in the caller's batch of each tile slot (bound arrays are indexed by it)
+  int32_t C;
   long long *dbg;            // development: per-CTA phase clocks (NULL = off)
   ScanLayout lay;
 };
-size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads);
+size_t adc_filter16_smem_bytes(int lut_stride, int k, int threads, int ti_clusters = 0);
 cudaError_t launch_adc_filter16_scan(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st);
 
 // nq_launch >= nq query slots are written (tile padding repeats the last query).  With plan.T == 8 and
@@ -290,7 +312,8 @@ cudaError_t launch_synth_codes(uint16_t *codes, int64_t n, int64_t global_row0, 
 // `scratch` (2 * nq * ceil(G/16) * k keys) is needed only when G > 16.
 cudaError_t launch_merge_keys(const uint64_t *keys_in, int64_t stride_l, int64_t stride_q, int G, int nq, int k,
                               int sqrt_flag, int hamming, int32_t *ids, void *dist, uint64_t *keys_out,
-                              const int32_t *id_map, int64_t id_base, uint64_t *scratch, cudaStream_t st);
+                              const int32_t *id_map, int64_t id_base, uint64_t *scratch, cudaStream_t st,
+                              const int32_t *qmap = nullptr);     // qmap: output slot of input query q (TI tile order)
 
 struct HamScanArgs {
   const uint4 *codes;        // packed tiles [tile][w][lane]
@@ -309,8 +332,13 @@ cudaError_t launch_ham_synth(uint4 *packed, int64_t n, int64_t row0, int64_t glo
 cudaError_t launch_refine(const float *xtrain, int64_t n, int D, const float *queries, int nq,
                           const int32_t *in_labels, int refine_num, int k, int32_t *labels, float *dists,
                           cudaStream_t st);
+// TI / visit planning for the filter kernels (ti_plan.cu)
+cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clusters, int C, int segdims, const int64_t *rule_size,
+                           float visit, int k, uint8_t *visited, int32_t *nearest, int32_t *perm, float *qperm, uint8_t *tmask,
+                           cudaStream_t st);
+cudaError_t launch_tile_clusters(const int64_t *start, int C, int64_t n_rows, uint16_t *tile_cl, cudaStream_t st);
 cudaError_t launch_rank_clusters(const float *q_proj, int nq, int D, const float *clusters, int C, int segdims,
-                                 const int64_t *start, const int64_t *size, float visit, int k, int2 *ranges,
-                                 int32_t *n_ranges, cudaStream_t st);
+                                 const int64_t *start, const int64_t *size, const int64_t *rule_size, float visit, int k,
+                                 int2 *ranges, int32_t *n_ranges, cudaStream_t st);
 
 }  // namespace vaqgpu

@@ -93,6 +93,16 @@ __global__ void __launch_bounds__(256, (W <= 2 ? 4 : 2)) ham_scan_kernel(const _
   for (; t < n_tiles; t += gstride, iter++) {
     const int tn = t + gstride;
     if (tn < n_tiles) load(nxt, tn);
+    {
+      // the register prefetch covers one tile; DRAM latency needs more bytes in flight per SM than that: pull the
+      // tile this warp reads six iterations from now into L2 (one 128-byte line per 8 lanes: lanes 0, 8, 16, 24 ask)
+      const int tp = t + 6 * gstride;
+      if (tp < n_tiles && (lane & 7) == 0) {
+        const uint4 *pp = a.codes + ((size_t)tp * W) * kTileRows + lane;
+#pragma unroll
+        for (int j = 0; j < W; j++) prefetch_l2(pp + j * kTileRows);
+      }
+    }
     const int row = t * kTileRows + lane;
     const bool valid = row < a.n_rows;
     if ((iter & 15) == 15) {

@@ -93,13 +93,16 @@ __global__ void __launch_bounds__(256) lut_scale_kernel(const float *__restrict_
   }
 }
 
-template <int T>
+// LC > 0: the subspace length is the compile-time constant LC — the centroid sits in registers and the dimension
+// loop is unrolled (ncu, round 2: the generic kernel issued 625 instructions per warp and was issue-bound at 61 %,
+// not memory-bound); LC == 0: any length.
+template <int T, int LC>
 __global__ void __launch_bounds__(256) lut_build_kernel(const float *__restrict__ q_proj, int nq, int D, const float *__restrict__ cent,
                                                         const __grid_constant__ LutPlan p,
                                                         float *__restrict__ lut, __half *__restrict__ lut16,
                                                         const float *__restrict__ scale) {
   const int qt = blockIdx.y;
-  const int L = p.L;
+  const int L = LC > 0 ? LC : p.L;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.total_entries) return;
   int lo = 0, hi = p.M;
@@ -111,6 +114,11 @@ __global__ void __launch_bounds__(256) lut_build_kernel(const float *__restrict_
   const int c = e - p.ent_off[s];
   const int K = p.ent_off[s + 1] - p.ent_off[s];
   const float *cp = cent + p.cent_off[s] + (size_t)c * L;
+  float cv[LC > 0 ? LC : 1];
+  if constexpr (LC > 0) {
+#pragma unroll
+    for (int j = 0; j < LC; j++) cv[j] = __ldg(cp + j);
+  }
   float acc[T];
 #pragma unroll
   for (int t = 0; t < T; t++) {
@@ -118,9 +126,17 @@ __global__ void __launch_bounds__(256) lut_build_kernel(const float *__restrict_
     const float *qs = q_proj + (size_t)q * D + (size_t)s * L;
     if (K >= 8) {
       float a = 0.f;
-      for (int j = 0; j < L; j++) {
-        const float d = __fsub_rn(__ldg(qs + j), __ldg(cp + j));
-        a = __fmaf_rn(d, d, a);
+      if constexpr (LC > 0) {
+#pragma unroll
+        for (int j = 0; j < LC; j++) {
+          const float d = __fsub_rn(__ldg(qs + j), cv[j]);
+          a = __fmaf_rn(d, d, a);
+        }
+      } else {
+        for (int j = 0; j < L; j++) {
+          const float d = __fsub_rn(__ldg(qs + j), __ldg(cp + j));
+          a = __fmaf_rn(d, d, a);
+        }
       }
       acc[t] = a;
     } else {
@@ -165,10 +181,17 @@ cudaError_t launch_lut_build(const float *q_proj, int nq, int nq_launch, int D, 
     lut_scale_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q_proj, nq, nq_pad, D, plan.M, plan.L, cent_rmax, scale);
   }
   switch (T) {
-    case 1: lut_build_kernel<1><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
-    case 2: lut_build_kernel<2><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
-    case 4: lut_build_kernel<4><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
-    case 8: lut_build_kernel<8><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, l16, scale); break;
+    case 1: lut_build_kernel<1, 0><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
+    case 2: lut_build_kernel<2, 0><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
+    case 4: lut_build_kernel<4, 0><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, nullptr, nullptr); break;
+    case 8:
+      switch (plan.L) {      // the subspace lengths of the BASELINE shapes get unrolled kernels
+#define LUT8(LCV) case LCV: lut_build_kernel<8, LCV><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, l16, scale); break;
+        LUT8(2) LUT8(3) LUT8(4) LUT8(6) LUT8(8) LUT8(12) LUT8(15) LUT8(16)
+#undef LUT8
+        default: lut_build_kernel<8, 0><<<grid, threads, 0, st>>>(q_proj, nq, D, centroids, plan, lut, l16, scale); break;
+      }
+      break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

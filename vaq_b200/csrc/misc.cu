@@ -71,8 +71,8 @@ cudaError_t launch_refine(const float *xtrain, int64_t n, int D, const float *qu
 // covered; empty clusters are skipped.  Emits (row_begin, row_end) ranges in visiting order.
 __global__ void rank_clusters_kernel(const float *__restrict__ q_proj, int D, const float *__restrict__ clusters,
                                      int C, int segdims, const int64_t *__restrict__ start,
-                                     const int64_t *__restrict__ size, float visit, int k, int2 *__restrict__ ranges,
-                                     int32_t *__restrict__ n_ranges) {
+                                     const int64_t *__restrict__ size, const int64_t *__restrict__ rule_size, float visit, int k,
+                                     int2 *__restrict__ ranges, int32_t *__restrict__ n_ranges) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *dist = reinterpret_cast<float *>(smem_raw);          // [C]
   int32_t *order = reinterpret_cast<int32_t *>(dist + C);      // [C]
@@ -103,10 +103,12 @@ __global__ void rank_clusters_kernel(const float *__restrict__ q_proj, int D, co
     bool enough = false;
     for (int cc = 0; (cc < maxVisit) || (!enough && cc < C); cc++) {
       const int cl = order[cc];
-      if (size[cl] == 0) continue;
-      ranges[(size_t)q * C + nr] = make_int2((int)start[cl], (int)(start[cl] + size[cl]));
-      nr++;
-      seen += size[cl];
+      if (rule_size[cl] == 0) continue;          // the rule counts the rows of the whole index (a row shard holds a part)
+      if (size[cl] > 0) {
+        ranges[(size_t)q * C + nr] = make_int2((int)start[cl], (int)(start[cl] + size[cl]));
+        nr++;
+      }
+      seen += rule_size[cl];
       if (seen >= k) enough = true;
     }
     n_ranges[q] = nr;
@@ -114,8 +116,8 @@ __global__ void rank_clusters_kernel(const float *__restrict__ q_proj, int D, co
 }
 
 cudaError_t launch_rank_clusters(const float *q_proj, int nq, int D, const float *clusters, int C, int segdims,
-                                 const int64_t *start, const int64_t *size, float visit, int k, int2 *ranges,
-                                 int32_t *n_ranges, cudaStream_t st) {
+                                 const int64_t *start, const int64_t *size, const int64_t *rule_size, float visit, int k,
+                                 int2 *ranges, int32_t *n_ranges, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   const size_t smem = (size_t)C * 8;
   static SmemOptIn optin;
@@ -123,7 +125,7 @@ cudaError_t launch_rank_clusters(const float *q_proj, int nq, int D, const float
     cudaError_t e = optin.ensure(rank_clusters_kernel, smem);
     if (e != cudaSuccess) return e;
   }
-  rank_clusters_kernel<<<nq, 256, smem, st>>>(q_proj, D, clusters, C, segdims, start, size, visit, k, ranges, n_ranges);
+  rank_clusters_kernel<<<nq, 256, smem, st>>>(q_proj, D, clusters, C, segdims, start, size, rule_size, visit, k, ranges, n_ranges);
   return cudaGetLastError();
 }
 

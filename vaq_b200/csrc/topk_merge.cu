@@ -20,10 +20,11 @@ struct MergeArgs {
   uint64_t *keys_out;
   const int32_t *id_map;
   int64_t id_base;
+  const int32_t *qmap;          // final outputs of input query q go to row qmap[q] (NULL: q)
 };
 
 __device__ __forceinline__ void emit(const MergeArgs &a, int q, int slot, uint64_t key) {
-  const size_t o = (size_t)q * a.k + slot;
+  const size_t o = (size_t)(a.qmap ? a.qmap[q] : q) * a.k + slot;
   if (key == kEmptyKey) {
     if (a.ids) a.ids[o] = -1;
     if (a.dist) {
@@ -87,9 +88,10 @@ __global__ void format_kernel(const __grid_constant__ MergeArgs a) {
 // 2 * nq * ceil(G/16) * k keys when G > 16 (may be NULL otherwise).
 cudaError_t launch_merge_keys(const uint64_t *keys_in, int64_t stride_l, int64_t stride_q, int G, int nq, int k,
                               int sqrt_flag, int hamming, int32_t *ids, void *dist, uint64_t *keys_out,
-                              const int32_t *id_map, int64_t id_base, uint64_t *scratch, cudaStream_t st) {
+                              const int32_t *id_map, int64_t id_base, uint64_t *scratch, cudaStream_t st, const int32_t *qmap) {
   if (nq <= 0 || k <= 0) return cudaSuccess;
   MergeArgs a{};
+  a.qmap = qmap;
   a.nq = nq; a.k = k; a.sqrt_flag = sqrt_flag; a.hamming = hamming;
   a.ids = ids; a.dist = dist; a.keys_out = keys_out; a.id_map = id_map; a.id_base = id_base;
   const int kFan = 16;

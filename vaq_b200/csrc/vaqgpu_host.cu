@@ -117,7 +117,9 @@ struct vaqgpu_index {
   int32_t C = 0, segdims = 0;
   float *d_clusters = nullptr;
   int64_t *d_cl_start = nullptr, *d_cl_size = nullptr;
+  int64_t *d_cl_rule = nullptr;    // cluster sizes the visiting rule counts (whole index; a row shard's own are smaller)
   int32_t *d_id_map = nullptr;
+  uint16_t *d_tile_cl = nullptr;   // cluster of each 32-row tile (filter kernels); NULL when the ranges are not an ascending partition
 
   // refine
   float *d_raw = nullptr;
@@ -141,7 +143,7 @@ struct vaqgpu_index {
   PeerBounds peers{};
   std::vector<void *> ipc_opened;
 
-  DevBuf w_lsrc, w_lscratch, w_dbg, w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
+  DevBuf w_vis, w_near, w_perm, w_qperm, w_tmask, w_lsrc, w_lscratch, w_dbg, w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
 };
 
 struct hamgpu_index {
@@ -195,7 +197,8 @@ cudaError_t grow_codes(uint4 **codes, int64_t *cap_rows, int64_t n_rows, int W, 
 // (a TI search must never silently skip the new rows), and so does a failed vaqgpu_set_clusters.
 void clear_clusters(vaqgpu_index *h) {
   cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_id_map);
-  h->d_clusters = nullptr; h->d_cl_start = h->d_cl_size = nullptr; h->d_id_map = nullptr;
+  cudaFree(h->d_cl_rule); cudaFree(h->d_tile_cl);
+  h->d_clusters = nullptr; h->d_cl_start = h->d_cl_size = h->d_cl_rule = nullptr; h->d_id_map = nullptr; h->d_tile_cl = nullptr;
   h->C = 0; h->segdims = 0;
 }
 
@@ -417,13 +420,12 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   const bool ea = (flags & VAQGPU_EA) != 0 || ti || !(flags & VAQGPU_HEAP);
   // HEAP (exhaustive) and EA return the same k best rows (VAQ.cpp:1718 vs :1750: same strict test, EA only skips
   // rows that cannot pass it), so both run the filter kernels; VAQGPU_SCAN_V1 keeps the literal exhaustive loop.
-  const bool filter = !ti && !(flags & VAQGPU_SCAN_V1) && h->n_rows > 0;
+  // TI / visit runs on the fp16 filter kernel too (row tiles of unvisited clusters are skipped) when the cluster
+  // ranges partition the rows in ascending order (what clusterTI produces) and the tables fit; otherwise, and under
+  // VAQGPU_SCAN_V1, it runs on the lane-per-row kernel over per-query row ranges.
+  bool filter = !(flags & VAQGPU_SCAN_V1) && h->n_rows > 0 && (!ti || (h->d_tile_cl && !(flags & VAQGPU_SCAN_F32)));
   const bool want_sqrt = (flags & VAQGPU_SQRT) != 0;
   int launches = 0;
-  {
-    int rc = filter ? ensure_layout(h, st) : ensure_rowid(h, st);
-    if (rc) return rc;
-  }
 
   if (record) CU(cudaEventRecord(h->ev[0], st));
   const float *d_qproj = d_queries;
@@ -439,6 +441,18 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
   ScanLayout lay;
   LutPlan plan;
   int32_t res_floats = 0, spill_floats = 0;
+
+  // ---- fp16 lower-bound tables, query tiles of 8 (default when eight queries' tables fit) -------------
+  bool filter16 = filter && !(flags & VAQGPU_SCAN_F32) && nq >= tune_knob("min16", 1);
+  if (filter16) {
+    apply_residency(h, (size_t)1 << 30, 8, lay, plan, res_floats, spill_floats);      // everything resident
+    if (adc_filter16_smem_bytes(plan.row_stride, k, 1024, ti ? h->C : 0) > kSmemCap) filter16 = false;
+  }
+  if (ti && !filter16) filter = false;          // TI without the fp16 kernel: lane-per-row kernel over row ranges
+  {
+    int rc = filter ? ensure_layout(h, st) : ensure_rowid(h, st);
+    if (rc) return rc;
+  }
 
   // Per-query bound array of this search (filter kernels).  With an exported array (row-sharded deployment) the
   // search uses one half and resets the other for the next search: peers only write a half between this shard's
@@ -462,18 +476,12 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     launches++;
   }
 
-  // ---- fp16 lower-bound tables, query tiles of 8 (default when eight queries' tables fit) -------------
-  bool filter16 = filter && !(flags & VAQGPU_SCAN_F32) && nq >= tune_knob("min16", 1);
-  if (filter16) {
-    apply_residency(h, (size_t)1 << 30, 8, lay, plan, res_floats, spill_floats);      // everything resident
-    if (adc_filter16_smem_bytes(plan.row_stride, k, 1024) > kSmemCap) filter16 = false;
-  }
   if (filter16) {
     // 32 warps x one row per lane (measured faster than 16 warps x two rows per lane at every chunk length: the scan
     // is bound by shared-memory wavefronts and issue slots, which more resident warps fill better; the 512-thread
     // variant stays selectable with VAQGPU_TUNE=threads=512)
     const int T = 8, threads = tune_knob("threads", 1024);
-    const size_t smem = adc_filter16_smem_bytes(plan.row_stride, k, threads);
+    const size_t smem = adc_filter16_smem_bytes(plan.row_stride, k, ti ? 1024 : threads, ti ? h->C : 0);
     const int nwarps = threads / 32;
     const size_t bytes_per_q = (size_t)plan.row_stride * 4;
     int qb_max = (int)std::max<size_t>(T, std::min<size_t>((size_t)nq, kLutWorkspaceBytes / bytes_per_q));
@@ -490,11 +498,26 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     CU(h->w_scale.ensure((size_t)qb_max * sizeof(float)));
     CU(h->w_keys.ensure((size_t)qb_max * out_slots * k * sizeof(uint64_t)));
     if (out_slots > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((out_slots + 15) / 16) * k * sizeof(uint64_t)));
+    if (ti) {
+      CU(h->w_vis.ensure((size_t)qb_max * h->C));
+      CU(h->w_near.ensure((size_t)qb_max * sizeof(int32_t)));
+      CU(h->w_perm.ensure((size_t)qb_max * sizeof(int32_t)));
+      CU(h->w_qperm.ensure((size_t)qb_max * h->D * sizeof(float)));
+      CU(h->w_tmask.ensure((size_t)(qb_max / T) * h->C));
+    }
 
     for (int q0 = 0; q0 < nq; q0 += qb_max) {
       const int qb = std::min(qb_max, nq - q0);
       const int qb_pad = (qb + T - 1) / T * T;
       const float *qp = d_qproj + (size_t)q0 * h->D;
+      if (ti) {
+        // which clusters each query visits, queries grouped into tiles by nearest cluster, per-(tile, cluster) masks
+        CU(launch_ti_plan(qp, qb, h->D, h->d_clusters, h->C, h->segdims, h->d_cl_rule ? h->d_cl_rule : h->d_cl_size, h->visit, k,
+                          (uint8_t *)h->w_vis.p, (int32_t *)h->w_near.p, (int32_t *)h->w_perm.p, (float *)h->w_qperm.p,
+                          (uint8_t *)h->w_tmask.p, st));
+        qp = (const float *)h->w_qperm.p;          // the batch in tile order
+        launches += 3;
+      }
       CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, h->d_cent_rmax, plan, (float *)h->w_lut.p, h->w_lut16.p,
                           (float *)h->w_scale.p, st));
       launches += 2;
@@ -511,7 +534,14 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       for (int i = 0; i < peers.n; i++) a.peers.p[i] += q0;
       a.seed = tune_knob("seed", 1);
       a.rowid = h->d_rowid;
+      if (ti) {
+        a.tile_cl = h->d_tile_cl; a.cl_start = h->d_cl_start; a.tmask = (const uint8_t *)h->w_tmask.p; a.C = h->C;
+        a.qmap = (const int32_t *)h->w_perm.p;
+        a.seed = 0;          // sample rows would have to be rows the query visits
+      }
       a.chunks_fast = tune_knob("chunks_fast", 0);
+      // a code matrix far larger than L2 streams from HBM: keep more of it in flight than the register prefetch holds
+      a.l2_prefetch = tune_knob("l2pf", (size_t)h->n_rows * lay.W * 16 > (size_t)(96u << 20) ? 4 : 0);
       a.lay = lay;
       const bool dbg = tune_knob("dbg", 0) != 0;
       const size_t n_cta = (size_t)((qb + T - 1) / T) * n_chunks;
@@ -529,9 +559,11 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       }
       launches++;
       if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
+      // TI: list q belongs to the query in slot q of the tile order -> written to that query's row; labels through id_map
       CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)out_slots * k, out_slots, qb, k, want_sqrt ? 1 : 0, 0,
                            d_labels ? d_labels + (size_t)q0 * k : nullptr, d_dists ? (void *)(d_dists + (size_t)q0 * k) : nullptr,
-                           d_keys ? d_keys + (size_t)q0 * k : nullptr, nullptr, h->id_base, (uint64_t *)h->w_scratch.p, st));
+                           d_keys ? d_keys + (size_t)q0 * k : nullptr, ti ? h->d_id_map : nullptr, h->id_base,
+                           (uint64_t *)h->w_scratch.p, st, ti ? (const int32_t *)h->w_perm.p : nullptr));
       launches += out_slots > 16 ? 2 : 1;
     }
     if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
@@ -541,7 +573,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     return VAQGPU_OK;
   }
 
-  if (filter) {
+  if (filter && !ti) {
     // ---- query-tile width T and residency -------------------------------------------------------
     const int threads = tune_knob("threads", 1024);
     int T = nq >= 8 ? 8 : (nq >= 3 ? 4 : nq);
@@ -646,7 +678,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     const int qb = std::min(qb_max, nq - q0);
     const float *qp = d_qproj + (size_t)q0 * h->D;
     if (ti) {
-      CU(launch_rank_clusters(qp, qb, h->D, h->d_clusters, h->C, h->segdims, h->d_cl_start, h->d_cl_size, h->visit, k,
+      CU(launch_rank_clusters(qp, qb, h->D, h->d_clusters, h->C, h->segdims, h->d_cl_start, h->d_cl_size, h->d_cl_rule ? h->d_cl_rule : h->d_cl_size, h->visit, k,
                               (int2 *)h->w_ranges.p, (int32_t *)h->w_nranges.p, st));
       launches++;
     }
@@ -766,12 +798,12 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_centroids); cudaFree(h->d_cent_rmax); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
-  cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size);
+  cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_cl_rule); cudaFree(h->d_tile_cl);
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_bounds);
   cudaFree(h->d_rowid);
-  for (DevBuf *b : {&h->w_lsrc, &h->w_lscratch, &h->w_dbg, &h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
+  for (DevBuf *b : {&h->w_vis, &h->w_near, &h->w_perm, &h->w_qperm, &h->w_tmask, &h->w_lsrc, &h->w_lscratch, &h->w_dbg, &h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
                     &h->w_labels, &h->w_dists, &h->w_outkeys, &h->w_cdf, &h->w_x})
     b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -1006,11 +1038,30 @@ int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t s
   if (e == cudaSuccess) e = up((void **)&h->d_cl_start, start, (size_t)C * sizeof(int64_t));
   if (e == cudaSuccess) e = up((void **)&h->d_cl_size, size, (size_t)C * sizeof(int64_t));
   if (e == cudaSuccess && id_map) e = up((void **)&h->d_id_map, id_map, (size_t)h->n_rows * sizeof(int32_t));
+  // filter-kernel TI needs the cluster of every row tile: possible when the ranges ascend without overlap (what
+  // clusterTI produces: start[c] = start[c-1] + size[c-1]); anything else keeps the lane-per-row kernel
+  bool ascending = C <= 0xFFFE && start[0] == 0 && start[C - 1] + size[C - 1] == h->n_rows;      // an exact partition
+  for (int c = 1; c < C && ascending; c++) ascending = start[c] == start[c - 1] + size[c - 1];
+  if (e == cudaSuccess && ascending) {
+    const int64_t n_tiles = (h->n_rows + kTileRows - 1) / kTileRows;
+    e = cudaMalloc(&h->d_tile_cl, (size_t)std::max<int64_t>(1, n_tiles) * sizeof(uint16_t));
+    if (e == cudaSuccess) e = launch_tile_clusters(h->d_cl_start, C, h->n_rows, h->d_tile_cl, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  }
   if (e != cudaSuccess) {
     clear_clusters(h);
     return fail(e == cudaErrorMemoryAllocation ? VAQGPU_ENOMEM : VAQGPU_ECUDA, "vaqgpu_set_clusters: %s", cudaGetErrorString(e));
   }
   h->C = C; h->segdims = segdims;
+  return VAQGPU_OK;
+}
+
+int vaqgpu_set_cluster_rule_sizes(vaqgpu_t *h, const int64_t *sizes) {
+  if (!h || !sizes) return fail(VAQGPU_EINVAL, "NULL argument");
+  if (!h->C) return fail(VAQGPU_ESTATE, "vaqgpu_set_clusters first");
+  DeviceGuard g(h->device);
+  if (!h->d_cl_rule) CU(cudaMalloc(&h->d_cl_rule, (size_t)h->C * sizeof(int64_t)));
+  CU(cudaMemcpy(h->d_cl_rule, sizes, (size_t)h->C * sizeof(int64_t), cudaMemcpyHostToDevice));
   return VAQGPU_OK;
 }
 

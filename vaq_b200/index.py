@@ -176,6 +176,10 @@ class VAQIndex:
         check(self.lib.vaqgpu_set_clusters(self.h, _vp(cl), cl.shape[0], cl.shape[1], _vp(st), _vp(sz),
                                            None if im is None else _vp(im)))
 
+    def set_cluster_rule_sizes(self, sizes):
+        sz = _c(sizes, np.int64)
+        check(self.lib.vaqgpu_set_cluster_rule_sizes(self.h, _vp(sz)))
+
     def set_visit(self, visit: float):
         check(self.lib.vaqgpu_set_visit(self.h, float(visit)))
 
