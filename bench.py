@@ -50,6 +50,10 @@ WORKLOADS = {
     "sift1m_256b_m32_min2max13_k10": dict(n=1_000_000, d=128, budget=256, M=32, min_bits=2, max_bits=13, nq=10_000, k=10, decay=4.0,
                                           source="vectors",
                                           desc="the reference's own SIFT1M setting (ExperimentsParameters.txt:55: 256 bit, 32 segments, min 2 / max 13 bits)"),
+    "sift1m_256b_m32_ti1000_k10": dict(n=1_000_000, d=128, budget=256, M=32, min_bits=7, max_bits=9, nq=10_000, k=10, decay=4.0,
+                                       source="vectors", ti_clusters=1000, ti_segments=16, visit=0.25,
+                                       desc="C2 model with the reference's SIFT1M TI setting (ExperimentsParameters.txt:55): 1000 TI clusters "
+                                            "over 16 segments, visit 25 % of the clusters; clustering on the device (vaqgpu_cluster_ti)"),
     "gist1m_512b_m64_k10": dict(n=1_000_000, d=960, budget=512, M=64, min_bits=4, max_bits=13, nq=1_000, k=10, decay=15.0,
                                 source="codes", train_rows=20_000,
                                 desc="BASELINE configs[2] (C3): GIST1M-shape 1M x 960, 1K queries, VAQ 512-bit m64 min4/max13 (large-LUT spill path)"),
@@ -218,15 +222,21 @@ def use_host_threads(n: int):
 # reference arm: the reference's own CPU search (compiled unmodified reference when available)
 # ---------------------------------------------------------------------------------------------
 
-def cpu_reference_search(model, codes, Q, k, seconds_target: float, threads: int):
-    """Times reference VAQ::search (EA mode, the reference's fastest exact mode) on a bounded sample of the query
-    batch against `codes`.  Returns (qps, n_queries, kind, labels, dists, seconds)."""
+def cpu_reference_search(model, codes, Q, k, seconds_target: float, threads: int, ti: dict | None = None):
+    """Times reference VAQ::search (EA mode, the reference's fastest exact mode; TI + EA over the given clusters when
+    `ti` is set) on a bounded sample of the query batch against `codes`.  Returns (qps, n_queries, kind, labels,
+    dists, seconds)."""
     from oracle import oracle as orc
     om = orc.Model(model.L, model.bits, model.centroids)
+    if ti is not None and not orc.Ref.available():
+        raise RuntimeError("the TI baseline needs the compiled reference (oracle/_ref)")
     if orc.Ref.available():
         kind = "reference"
-        rv = orc.Ref().vaq(om, orc.NN_EA)
+        rv = orc.Ref().vaq(om, orc.NN_EA | (orc.NN_TI if ti is not None else 0))
         rv.set_codes(codes)
+        if ti is not None:
+            rv.set_ti(ti["clusters"], ti["start"], ti["sizes"], ti["members"], ti["code_to_cc"])
+            rv.set_visit(ti["visit"])
 
         def run(q):
             return rv.search(q, k, nthreads=threads)
@@ -351,6 +361,15 @@ def run_gpu_arm(args, w, name):
     torch.cuda.synchronize()
     log(f"[bench] rank {rank}: rows [{sh.lo},{sh.hi}) resident in {time.time() - t0:.1f}s; row_bytes={sh.index.row_bytes}")
     ix = sh.index
+    if w.get("ti_clusters"):
+        if world > 1:
+            raise SystemExit("the TI workload runs on one GPU in this bench (sharded TI: tests/test_gpu_sharded.py)")
+        from vaq_b200.index import SQRT, TI
+        t0 = time.time()
+        ix.cluster_ti(w["ti_clusters"], w["ti_segments"], 10)
+        ix.set_visit(w["visit"])
+        flags = TI | EA | SQRT | PROJECTED
+        log(f"[bench] device clusterTI: {w['ti_clusters']} clusters over {w['ti_segments']} segments in {time.time() - t0:.2f}s")
     exchange = False
     if world > 1 and not args.no_bound_exchange:
         exchange = sh.enable_bound_exchange(nq)
@@ -607,15 +626,38 @@ def run_gpu_arm(args, w, name):
         om = orc.Model(model.L, model.bits, model.centroids)
         glab_all, gdis_all = lab_pin.numpy(), dis_pin.numpy()
         if w["source"] == "vectors":
-            codes, rows_used, how = reference_codes(pb, args.cpu_rows)      # VAQ::encode of the compiled reference, all rows
             parity = {}
-            if world == 1:
-                mine = ix.get_codes()
-                parity["device_encode_vs_reference_encode_mismatches"] = int((mine != codes).sum())
-                parity["codes_compared"] = int(codes.size)
-            qps, n_used, kind, rlab, rdis, dt = cpu_reference_search(model, codes, Q, k, args.cpu_seconds, threads)
+            ti_ref = None
+            if w.get("ti_clusters"):
+                # the reference's own searchTriangleInequality on the clusters the device built: rows of a cluster sorted
+                # far -> near the centre (VAQ.cpp:968-982), codeToCC by original id
+                ti = ix.get_clusters()
+                grouped = ix.get_codes()
+                seg = w["ti_segments"]
+                dec = np.concatenate([model.centroids[s_][grouped[:, s_]] for s_ in range(seg)], axis=1)
+                cl_of = np.repeat(np.arange(ti["clusters"].shape[0]), ti["sizes"])
+                c2c = np.sqrt(((dec - ti["clusters"][cl_of]) ** 2).sum(1)).astype(np.float32)
+                order = np.lexsort((np.arange(c2c.size), -c2c, cl_of))
+                c2c_by_id = np.empty_like(c2c)
+                c2c_by_id[ti["members"][order]] = c2c[order]
+                codes = grouped[order]
+                ti_ref = dict(clusters=ti["clusters"], start=ti["start"], sizes=ti["sizes"], members=ti["members"][order],
+                              code_to_cc=c2c_by_id, visit=w["visit"])
+            else:
+                codes, rows_used, how = reference_codes(pb, args.cpu_rows)      # VAQ::encode of the compiled reference, all rows
+                if world == 1:
+                    mine = ix.get_codes()
+                    diff = np.nonzero((mine != codes).any(1))[0]
+                    parity["device_encode_vs_reference_encode_mismatches"] = int((mine != codes).sum())
+                    parity["codes_compared"] = int(codes.size)
+                    if diff.size:       # float near-ties between two centroids (Eigen's reduction order)
+                        _, margin = orc.Port().encode(om, pb.XP[diff], with_margin=True)
+                        bad = mine[diff] != codes[diff]
+                        parity["mismatch_margin_max"] = float(margin[bad].max())     # gap between the two centroids' distances
+            qps, n_used, kind, rlab, rdis, dt = cpu_reference_search(model, codes, Q, k, args.cpu_seconds, threads, ti=ti_ref)
             cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind,
-                   "sample": f"{n_used} of {nq} queries, all {n} rows, EA mode, query-sliced over {threads} threads, {dt:.1f}s"}
+                   "sample": f"{n_used} of {nq} queries, all {n} rows, {'TI+EA mode on the device-built clusters' if ti_ref else 'EA mode'}, "
+                             f"query-sliced over {threads} threads, {dt:.1f}s"}
             glab, gdis = glab_all[:n_used], gdis_all[:n_used]
             gt = synth.brute_force_knn(pb.X, pb.Qraw[:min(n_used, 200)], min(k, 10))
             kk = min(k, 10)
@@ -655,7 +697,8 @@ def run_gpu_arm(args, w, name):
         "metric": "queries/sec at recall@10", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(name, w, "EA"), row_bytes=row_bytes,
+        "config": dict(workload_config(name, w, "TI+EA, visit %.2f of %d clusters" % (w["visit"], w["ti_clusters"]) if w.get("ti_clusters") else "EA"),
+                       row_bytes=row_bytes,
                        sharding=f"rows/{sh.R}" + (f" x queries/{sh.qgroups} (matrix replicated {sh.qgroups}x)" if sh.qgroups > 1 else ""),
                        rows_per_gpu=n_local, bound_exchange="nvlink peer memory" if exchange else "off",
                        l2="256 MB fill between timed steps", source=w["source"], desc=w["desc"], scan_config=cfg),

@@ -148,6 +148,16 @@ int vaqgpu_bounds_attach_ptr(vaqgpu_t *h, int32_t n_peers, void *const *peer_ptr
  * until at least k rows were scanned. */
 int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t segdims,
                         const int64_t *start, const int64_t *size, const int32_t *id_map);
+/* replaces VAQ::clusterTI itself (VAQ.cpp:878-999) on the device: k-means (`iters` Lloyd iterations from evenly
+ * spaced rows; 0 = assign to the seed rows only, as useKMeans = false) over the rows decoded in their first
+ * n_segments subspaces (<= 0: all, mTISegmentNum = -1), rows regrouped by cluster in place (stable), cluster ranges and
+ * the original id of every regrouped row kept on the device.  Equivalent to vaqgpu_set_clusters with the result.
+ * Clustering parity with the reference is unpinned (it calls Armadillo's kmeans); searches over the clusters are exact.
+ * vaqgpu_get_clusters reads the clustering back (any output may be NULL; clusters [C x segdims], start/size [C],
+ * id_map [rows]). */
+int vaqgpu_cluster_ti(vaqgpu_t *h, int32_t C, int32_t n_segments, int32_t iters);
+int vaqgpu_get_clusters(vaqgpu_t *h, int32_t *C, int32_t *segdims, float *clusters, int64_t *start, int64_t *size,
+                        int32_t *id_map);
 int vaqgpu_set_visit(vaqgpu_t *h, float visit);
 /* Row-sharded TI: a shard's vaqgpu_set_clusters holds the part of each cluster that falls into its rows; the visiting
  * rule ("continue while fewer than k rows were covered", VAQ.cpp:1555,1616-1618) must count the clusters' sizes in the

@@ -370,6 +370,14 @@ class RefVAQ:
                                 _ptr(x, C.c_float), C.c_long(x.shape[0]), k, _ptr(labels, C.c_int), _ptr(dists, C.c_float))
         return labels, dists
 
+    def set_ti(self, clusters, start, sizes, members, code_to_cc):
+        """clusters [C, segdims]; start/sizes [C]; members: ids in regrouped order (far -> near inside a cluster);
+        code_to_cc indexed by original id.  The codebook must already hold the regrouped rows (set_codes)."""
+        cl = _f32(clusters); st = np.ascontiguousarray(start, np.int32); sz = np.ascontiguousarray(sizes, np.int32)
+        mem = np.ascontiguousarray(members, np.int32); c2c = _f32(code_to_cc)
+        self.lib.ref_vaq_set_ti(self.h, _ptr(cl, C.c_float), int(cl.shape[0]), int(cl.shape[1]), _ptr(st, C.c_int),
+                                    _ptr(sz, C.c_int), _ptr(mem, C.c_int), _ptr(c2c, C.c_float), C.c_long(c2c.size))
+
     def cluster_ti(self, n_clusters: int, n_segments: int = -1, use_kmeans: bool = False, seed: int = 1) -> dict:
         self.lib.ref_vaq_cluster_ti(self.h, n_clusters, n_segments, int(use_kmeans), seed)
         segdims = self.lib.ref_vaq_ti_segdims(self.h)

@@ -190,6 +190,28 @@ void ref_vaq_cluster_ti(void *h, int n_clusters, int n_segments, int use_kmeans,
   v->clusterTI(use_kmeans != 0, false);
 }
 
+/* Hand the reference a clustering made elsewhere — its own public TI members (VAQ.hpp:77-84) filled the way
+ * clusterTI leaves them: centres [C x segdims], start idx / sizes [C], member ids in regrouped row order (each cluster's
+ * members sorted far -> near its centre, VAQ.cpp:968-982), codeToCC by ORIGINAL id.  mCodebook must be set to the
+ * regrouped rows (ref_vaq_set_codes).  Lets bench.py run the reference's searchTriangleInequality on the clusters the
+ * device built. */
+void ref_vaq_set_ti(void *h, const float *clusters, int C, int segdims, const int *start_idx, const int *sizes, const int *members,
+                    const float *code_to_cc, long n) {
+  VAQ *v = static_cast<VAQ *>(h);
+  v->mTIClusterNum = C;
+  v->mTISegmentNum = segdims / v->mSubsLen;
+  v->mTIVariance = 1.f;
+  v->mTIClusters = Eigen::Map<const RowMatrixXf>(clusters, C, segdims);
+  v->mClusterMembersStartIdx.assign(start_idx, start_idx + C);
+  v->mTIClustersMember.assign((size_t)C, std::vector<int>());
+  long pos = 0;
+  for (int c = 0; c < C; c++) {
+    v->mTIClustersMember[(size_t)c].assign(members + pos, members + pos + sizes[c]);
+    pos += sizes[c];
+  }
+  v->mCodeToCCDist.assign(code_to_cc, code_to_cc + n);
+}
+
 int ref_vaq_ti_segdims(void *h) {
   VAQ *v = static_cast<VAQ *>(h);
   return v->mTISegmentNum * v->mSubsLen;

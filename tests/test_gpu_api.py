@@ -77,7 +77,7 @@ def test_ti_visit_flow():
     # visit = 0.25: top-k over the rows of the nearest quarter of the clusters
     vaq.mVisit = 0.25
     part = vaq.search(Q, 10, projected=True)
-    ti = vaq._ti
+    ti = vaq.ti_state
     cd = np.sqrt(((Q[:, None, :ti["clusters"].shape[1]] - ti["clusters"][None]) ** 2).sum(-1))
     for q in range(Q.shape[0]):
         vis = np.argsort(cd[q], kind="stable")[:16]
@@ -86,6 +86,41 @@ def test_ti_visit_flow():
         d = orc.Port().adc_all(om, lut, codes[rows])
         order = np.lexsort((rows, d))[:10]
         assert set(part.labels[q].tolist()) == set(rows[order].tolist()), q
+
+
+def test_device_cluster_ti_is_a_stable_nearest_centre_partition():
+    """vaqgpu_cluster_ti (VAQ::clusterTI on the device): every row sits in the cluster of its nearest centre (distance
+    between the row decoded in the leading segments and the centre), rows keep their order inside a cluster, the
+    ranges partition the rows, two runs give the same bits, and the regrouped matrix holds the same rows."""
+    from vaq_b200.index import VAQIndex
+    rng = np.random.default_rng(12)
+    bits = np.array([8, 8, 7, 7, 6, 6, 5, 5], np.int32)
+    L, seg, C = 3, 4, 37
+    cents = [rng.standard_normal((1 << int(b), L)).astype(np.float32) for b in bits]
+    n = 30011
+    codes = np.stack([rng.integers(0, 1 << int(b), size=n) for b in bits], 1).astype(np.uint16)
+    outs = []
+    for _ in range(2):
+        ix = VAQIndex(L, bits, cents)
+        ix.add_codes(codes)
+        ix.cluster_ti(C, seg, 5)
+        ti = ix.get_clusters()
+        outs.append((ti, ix.get_codes()))
+        ix.close()
+    (ti, grouped), (ti2, grouped2) = outs
+    for key in ("clusters", "start", "sizes", "members"):
+        assert np.array_equal(ti[key], ti2[key]), f"{key} differs between two runs"
+    assert np.array_equal(grouped, grouped2)
+    assert ti["clusters"].shape == (C, seg * L)
+    assert ti["sizes"].sum() == n and ti["start"][0] == 0 and np.array_equal(ti["start"][1:], np.cumsum(ti["sizes"])[:-1])
+    assert np.array_equal(np.sort(ti["members"]), np.arange(n))
+    assert np.array_equal(grouped, codes[ti["members"]])                       # the rows moved with their ids
+    dec = np.concatenate([cents[s][codes[:, s]] for s in range(seg)], axis=1).astype(np.float64)
+    d = ((dec[:, None, :] - ti["clusters"][None].astype(np.float64)) ** 2).sum(-1)
+    for c in range(C):
+        mem = ti["members"][ti["start"][c]:ti["start"][c] + ti["sizes"][c]]
+        assert (np.diff(mem) > 0).all()                                        # stable: original order inside a cluster
+        assert (d[mem, c] <= d[mem].min(1) * (1 + 1e-5) + 1e-6).all()          # nearest centre (fp32 vs fp64 slack)
 
 
 def test_bitvecengine_flow():

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "vaqgpu_bounds_attach_ipc": (C.c_int, [_p, _i32, _p]),
     "vaqgpu_bounds_attach_ptr": (C.c_int, [_p, _i32, C.POINTER(_p)]),
     "vaqgpu_set_clusters": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p]),
+    "vaqgpu_cluster_ti": (C.c_int, [_p, _i32, _i32, _i32]),
+    "vaqgpu_get_clusters": (C.c_int, [_p, C.POINTER(_i32), C.POINTER(_i32), _p, _p, _p, _p]),
     "vaqgpu_set_visit": (C.c_int, [_p, _f]),
     "vaqgpu_set_cluster_rule_sizes": (C.c_int, [_p, _p]),
     "vaqgpu_set_raw_vectors": (C.c_int, [_p, _p, _i64, _i32]),

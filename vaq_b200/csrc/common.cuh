@@ -337,6 +337,14 @@ cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clus
                            float visit, int k, uint8_t *visited, int32_t *nearest, int32_t *perm, float *qperm, uint8_t *tmask,
                            cudaStream_t st);
 cudaError_t launch_tile_clusters(const int64_t *start, int C, int64_t n_rows, uint16_t *tile_cl, cudaStream_t st);
+// device-side clusterTI (cluster_ti.cu)
+size_t cluster_ti_table_floats(const LutPlan &plan, int seg, int C);
+size_t regroup_hist_ints(int64_t n, int C);
+cudaError_t launch_cluster_ti_kmeans(const uint4 *codes, const ScanLayout &lay, int64_t n, const LutPlan &plan, int seg,
+                                     const float *cent, const int32_t *d_cent_off, const int32_t *d_ent_off, int C, int iters,
+                                     float *centres, float *T, int32_t *hist, int32_t *assign, int32_t *sizes, cudaStream_t st);
+cudaError_t launch_regroup(const int32_t *assign, const int32_t *sizes, int64_t n, int C, const uint4 *src, uint4 *dst, int W,
+                           int32_t *id_map, int64_t *start, int64_t *size64, int32_t *bh, cudaStream_t st);
 cudaError_t launch_rank_clusters(const float *q_proj, int nq, int D, const float *clusters, int C, int segdims,
                                  const int64_t *start, const int64_t *size, const int64_t *rule_size, float visit, int k,
                                  int2 *ranges, int32_t *n_ranges, cudaStream_t st);

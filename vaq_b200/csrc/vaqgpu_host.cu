@@ -108,7 +108,7 @@ struct vaqgpu_index {
   float *d_centroids = nullptr;
   float *d_cent_rmax = nullptr;   // [M] largest centroid norm per subspace (fp16 table scaling)
   float *d_eig = nullptr;
-  int32_t *d_bits = nullptr, *d_ent_off = nullptr;
+  int32_t *d_bits = nullptr, *d_ent_off = nullptr, *d_cent_off = nullptr;
 
   uint4 *d_codes = nullptr;
   int64_t n_rows = 0, cap_rows = 0;
@@ -786,6 +786,8 @@ int vaqgpu_create(const vaqgpu_model_desc *m, int device, vaqgpu_t **out) {
   CUX(cudaMemcpy(h->d_bits, m->bits, m->M * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUX(cudaMalloc(&h->d_ent_off, (m->M + 1) * sizeof(int32_t)));
   CUX(cudaMemcpy(h->d_ent_off, h->plan.ent_off, (m->M + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUX(cudaMalloc(&h->d_cent_off, m->M * sizeof(int32_t)));
+  CUX(cudaMemcpy(h->d_cent_off, h->plan.cent_off, m->M * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUX(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto &e : h->ev) CUX(cudaEventCreate(&e));
 #undef CUX
@@ -797,7 +799,7 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   if (!h) return;
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_centroids); cudaFree(h->d_cent_rmax); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off);
+  cudaFree(h->d_centroids); cudaFree(h->d_cent_rmax); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off); cudaFree(h->d_cent_off);
   cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_cl_rule); cudaFree(h->d_tile_cl);
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -1053,6 +1055,97 @@ int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t s
     return fail(e == cudaErrorMemoryAllocation ? VAQGPU_ENOMEM : VAQGPU_ECUDA, "vaqgpu_set_clusters: %s", cudaGetErrorString(e));
   }
   h->C = C; h->segdims = segdims;
+  return VAQGPU_OK;
+}
+
+__global__ void compose_ids_kernel(const int32_t *__restrict__ older, int32_t *__restrict__ ids, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = older[ids[i]];
+}
+
+int vaqgpu_cluster_ti(vaqgpu_t *h, int32_t C, int32_t n_segments, int32_t iters) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  if (h->n_rows <= 0) return fail(VAQGPU_ESTATE, "vaqgpu_cluster_ti on an empty index");
+  if (C < 1 || C > 0xFFFE || C > h->n_rows) return fail(VAQGPU_EINVAL, "C=%d (1..min(65534, rows))", C);
+  if (iters < 0 || iters > 1000) return fail(VAQGPU_EINVAL, "iters=%d", iters);
+  const int seg = (n_segments <= 0 || n_segments > h->M) ? h->M : n_segments;
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  int rc = restore_layout(h, st);          // ids of the regrouped rows are expressed in the arrival order
+  if (rc) return rc;
+  // a second clustering of an already regrouped index composes the id maps
+  int32_t *old_map = h->d_id_map;
+  h->d_id_map = nullptr;
+  clear_clusters(h);
+  const int64_t n = h->n_rows;
+  const size_t tbl = cluster_ti_table_floats(h->plan, seg, C);
+  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+  float *centres = nullptr, *T = nullptr;
+  int32_t *hist = nullptr, *assign = nullptr, *sizes = nullptr, *bh = nullptr, *id_map = nullptr;
+  int64_t *start = nullptr, *size64 = nullptr;
+  uint4 *ncodes = nullptr;
+  uint16_t *tile_cl = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(centres); cudaFree(T); cudaFree(hist); cudaFree(assign); cudaFree(sizes); cudaFree(bh); cudaFree(id_map);
+    cudaFree(start); cudaFree(size64); cudaFree(ncodes); cudaFree(tile_cl); cudaFree(old_map);
+  };
+#define CT(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      cleanup();                                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? VAQGPU_ENOMEM : VAQGPU_ECUDA, "vaqgpu_cluster_ti: %s: %s", #call, cudaGetErrorString(e_)); \
+    }                                                                                                    \
+  } while (0)
+  CT(cudaMalloc(&centres, (size_t)C * seg * h->L * sizeof(float)));
+  CT(cudaMalloc(&T, tbl * sizeof(float)));
+  CT(cudaMalloc(&hist, tbl * sizeof(int32_t)));
+  CT(cudaMalloc(&assign, (size_t)n * sizeof(int32_t)));
+  CT(cudaMalloc(&sizes, (size_t)C * sizeof(int32_t)));
+  CT(cudaMalloc(&bh, regroup_hist_ints(n, C) * sizeof(int32_t)));
+  CT(cudaMalloc(&id_map, (size_t)n * sizeof(int32_t)));
+  CT(cudaMalloc(&start, (size_t)C * sizeof(int64_t)));
+  CT(cudaMalloc(&size64, (size_t)C * sizeof(int64_t)));
+  CT(cudaMalloc(&ncodes, (size_t)tiles * kTileRows * h->lay.W * sizeof(uint4)));
+  CT(cudaMalloc(&tile_cl, (size_t)tiles * sizeof(uint16_t)));
+  CT(cudaMemsetAsync(ncodes, 0, (size_t)tiles * kTileRows * h->lay.W * sizeof(uint4), st));
+  CT(launch_cluster_ti_kmeans(h->d_codes, h->lay, n, h->plan, seg, h->d_centroids, h->d_cent_off, h->d_ent_off, C, iters, centres, T, hist,
+                              assign, sizes, st));
+  CT(launch_regroup(assign, sizes, n, C, h->d_codes, ncodes, h->lay.W, id_map, start, size64, bh, st));
+  if (old_map) {
+    compose_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(old_map, id_map, n);
+    CT(cudaGetLastError());
+  }
+  CT(launch_tile_clusters(start, C, n, tile_cl, st));
+  CT(cudaStreamSynchronize(st));
+#undef CT
+  cudaFree(h->d_codes);
+  h->d_codes = ncodes; ncodes = nullptr;
+  h->cap_rows = tiles * kTileRows;
+  h->d_clusters = centres; centres = nullptr;
+  h->d_cl_start = start; start = nullptr;
+  h->d_cl_size = size64; size64 = nullptr;
+  h->d_id_map = id_map; id_map = nullptr;
+  h->d_tile_cl = tile_cl; tile_cl = nullptr;
+  h->C = C; h->segdims = seg * h->L;
+  h->opt_n = 0;
+  cleanup();
+  return VAQGPU_OK;
+}
+
+int vaqgpu_get_clusters(vaqgpu_t *h, int32_t *C, int32_t *segdims, float *clusters, int64_t *start, int64_t *size, int32_t *id_map) {
+  if (!h) return fail(VAQGPU_EINVAL, "handle is NULL");
+  if (C) *C = h->C;
+  if (segdims) *segdims = h->segdims;
+  if (!h->C) return (clusters || start || size || id_map) ? fail(VAQGPU_ESTATE, "no clusters set") : VAQGPU_OK;
+  DeviceGuard g(h->device);
+  if (clusters) CU(cudaMemcpy(clusters, h->d_clusters, (size_t)h->C * h->segdims * sizeof(float), cudaMemcpyDeviceToHost));
+  if (start) CU(cudaMemcpy(start, h->d_cl_start, (size_t)h->C * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (size) CU(cudaMemcpy(size, h->d_cl_size, (size_t)h->C * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (id_map) {
+    if (!h->d_id_map) return fail(VAQGPU_ESTATE, "clusters were set without an id map");
+    CU(cudaMemcpy(id_map, h->d_id_map, (size_t)h->n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
   return VAQGPU_OK;
 }
 

@@ -176,6 +176,20 @@ class VAQIndex:
         check(self.lib.vaqgpu_set_clusters(self.h, _vp(cl), cl.shape[0], cl.shape[1], _vp(st), _vp(sz),
                                            None if im is None else _vp(im)))
 
+    def cluster_ti(self, C_: int, n_segments: int = -1, iters: int = 10):
+        """VAQ::clusterTI on the device: k-means over the decoded leading segments, rows regrouped by cluster."""
+        check(self.lib.vaqgpu_cluster_ti(self.h, int(C_), int(n_segments), int(iters)))
+
+    def get_clusters(self, with_id_map: bool = True) -> dict:
+        nc, sd = C.c_int32(0), C.c_int32(0)
+        check(self.lib.vaqgpu_get_clusters(self.h, C.byref(nc), C.byref(sd), None, None, None, None))
+        cl = np.empty((nc.value, sd.value), np.float32)
+        st = np.empty(nc.value, np.int64)
+        sz = np.empty(nc.value, np.int64)
+        im = np.empty(self.num_rows, np.int32) if with_id_map else None
+        check(self.lib.vaqgpu_get_clusters(self.h, None, None, _vp(cl), _vp(st), _vp(sz), None if im is None else _vp(im)))
+        return dict(clusters=cl, start=st, sizes=sz, members=im)
+
     def set_cluster_rule_sizes(self, sizes):
         sz = _c(sizes, np.int64)
         check(self.lib.vaqgpu_set_cluster_rule_sizes(self.h, _vp(sz)))

@@ -17,6 +17,15 @@ def shard_bounds(n_rows: int, world: int) -> list[int]:
     return [min(r * per, n_rows) for r in range(world + 1)]
 
 
+def local_cluster_ranges(start, sizes, lo: int, hi: int):
+    """Intersection of the cluster row ranges [start, start+size) with the shard's rows [lo, hi), relative to lo."""
+    start = np.ascontiguousarray(start, np.int64)
+    sizes = np.ascontiguousarray(sizes, np.int64)
+    a = np.clip(start, lo, hi)
+    b = np.clip(start + sizes, lo, hi)
+    return (a - lo).astype(np.int64), (b - a).astype(np.int64)
+
+
 def make_keys_f32(dist: np.ndarray, ids: np.ndarray) -> np.ndarray:
     """(float32 distance bits << 32) | uint32 id — the key format of the scan kernels (host restatement
     used by tests and by callers that post-process gathered keys)."""
@@ -111,6 +120,15 @@ class ShardedVAQ:
 
     def add_synthetic(self, seed: int, cdf=None):
         self.index.add_synthetic(self.hi - self.lo, seed, cdf)
+
+    def set_clusters_global(self, clusters, start, sizes, id_map=None):
+        """TI / visit on a row-sharded index: the cluster ranges of the whole (cluster-grouped) matrix are
+        split at the shard boundaries — this rank keeps the intersection of every range with its rows — while the
+        visiting rule keeps counting the clusters' sizes in the whole index."""
+        st, sz = local_cluster_ranges(start, sizes, self.lo, self.hi)
+        im = None if id_map is None else np.ascontiguousarray(id_map, np.int32)[self.lo:self.hi]
+        self.index.set_clusters(clusters, st, sz, im)
+        self.index.set_cluster_rule_sizes(np.ascontiguousarray(sizes, np.int64))
 
     def query_slice(self, nq: int) -> tuple[int, int]:
         """Queries [a, b) this rank's replica group answers (equal slices, padded at the end)."""

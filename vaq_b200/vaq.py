@@ -97,27 +97,21 @@ class VAQ:
     def set_codebook(self, codes: np.ndarray) -> None:
         self.index.add_codes(codes)
 
-    # VAQ::clusterTI, VAQ.cpp:878-999: k-means over the decoded leading dims, rows regrouped by cluster.
-    # (Host-side, like training.  The reference also sorts each cluster far->near for its break test,
-    # VAQ.cpp:968-982; the device scan is exhaustive inside a visited cluster, so the order is irrelevant.)
-    def clusterTI(self, useKMeans: bool = True, verbose: bool = False) -> None:
-        m = self.model
+    # VAQ::clusterTI, VAQ.cpp:878-999, on the device (csrc/cluster_ti.cu): k-means over the rows decoded in their leading
+    # mTISegmentNum segments, rows regrouped by cluster, cluster ranges + original ids kept in HBM.  (The reference also
+    # sorts each cluster far->near for its break test, VAQ.cpp:968-982; the device scan is exhaustive inside a visited
+    # cluster, so that order is irrelevant.)
+    def clusterTI(self, useKMeans: bool = True, verbose: bool = False, iters: int = 10) -> None:
         C = self.mTIClusterNum
         if C <= 0:
             raise ValueError("set mTIClusterNum (method string ...,EA_TI<c>) first")
-        seg = m.M if self.mTISegmentNum in (-1, 0) else self.mTISegmentNum
-        codes = self.index.get_codes()
-        dec = np.concatenate([m.centroids[s][codes[:, s]] for s in range(seg)], axis=1)
-        cent = host_train.kmeans(dec, C, 10 if useKMeans else 0)
-        d = ((dec ** 2).sum(1)[:, None] - 2.0 * dec @ cent.T + (cent ** 2).sum(1)[None, :])
-        assign = d.argmin(1)
-        order = np.argsort(assign, kind="stable")
-        sizes = np.bincount(assign, minlength=C).astype(np.int64)
-        start = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
-        self._new_index()
-        self.index.add_codes(codes[order])
-        self.index.set_clusters(cent, start, sizes, order.astype(np.int32))
-        self._ti = dict(clusters=cent, start=start, sizes=sizes, members=order)
+        self.index.cluster_ti(C, self.mTISegmentNum, iters if useKMeans else 0)
+        self._ti = True
+
+    # clusterTI's outputs as the reference holds them (VAQ.hpp:77-84), read back from the device
+    @property
+    def ti_state(self) -> dict:
+        return self.index.get_clusters()
 
     # VAQ::search, VAQ.cpp:776-847
     def search(self, XTest: np.ndarray, k: int, verbose: bool = False, projected: bool = False) -> LabelDistVecF:
