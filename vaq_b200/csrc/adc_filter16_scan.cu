@@ -218,6 +218,11 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
     if (tile_begin + warp + u * nwarps < tile_end) cur[u] = ldg_stream_u4(pnext - (TPI - u) * pstep);
     if (tile_begin + warp + (TPI + u) * nwarps < tile_end) nxt[u] = ldg_stream_u4(pnext + u * pstep);
   }
+  uint32_t ci_cur = 0u, ci_nxt = 0u;      // TI: cluster of this warp's current / next row tile
+  if constexpr (TI) {
+    if (tile_begin + warp < tile_end) ci_cur = (uint32_t)__ldg(a.tile_cl + tile_begin + warp);
+    if (tile_begin + warp + nwarps < tile_end) ci_nxt = (uint32_t)__ldg(a.tile_cl + tile_begin + warp + nwarps);
+  }
   int refresh = 0;
   const uint32_t rows_here = (uint32_t)(min(a.n_rows, tile_end << 5) - row_base);    // valid rows of this chunk
 
@@ -233,7 +238,10 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   // Sample rows per lane: at most a quarter of the chunk.  (A smaller sample on short chunks was measured slower: the
   // looser seed costs more in the first passes than the sampling saves.)  A CTA whose queries all arrive with a bound
   // (later row chunks of a query tile, or bounds already published by other shards) skips the seeding altogether.
-  const int spl = (int)min(4u, rows_here / (blockDim.x * 4u));
+  // A search of one or two query tiles over many chunks (the HBM-bound regime) runs all its CTAs at once on the same
+  // queries: their exact bounds pool through thr_global within microseconds, so a quarter of the sample is enough.
+  const unsigned grid_chunks = a.chunks_fast ? gridDim.x : gridDim.y, grid_qtiles = a.chunks_fast ? gridDim.y : gridDim.x;
+  const int spl = (int)min((grid_chunks >= 32u && grid_qtiles <= 2u) ? 1u : 4u, rows_here / (blockDim.x * 4u));
   int unbounded = 0;
   if (tid < T8 && q0 + tid < a.nq) unbounded = thr_f[tid] == 0xFFFFFFFFu;
   if (!TI && a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64 && __syncthreads_or(unbounded)) {
@@ -364,7 +372,9 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
           unsigned cm = 0xFFu;          // queries of the tile that visit this row's cluster
           if constexpr (TI) {
             const int itu = it + u * nwarps;
-            const uint32_t ci = itu < n_it ? (uint32_t)__ldg(a.tile_cl + tile_begin + itu) : 0u;
+            const uint32_t ci = ci_cur;          // loaded one iteration ago (TPI == 1 in TI mode)
+            ci_cur = ci_nxt;
+            ci_nxt = itu + 2 * nwarps < n_it ? (uint32_t)__ldg(a.tile_cl + tile_begin + itu + 2 * nwarps) : 0u;
             if (ci != 0xFFFFu) cm = smask[ci];
             else cm = smask[cluster_of_row(a.cl_start, a.C, row_base + ((int64_t)itu << 5) + lane)];
             if (!__any_sync(0xffffffffu, cm != 0u)) { sb[u] = 0u; continue; }          // nobody visits: no gathers
@@ -610,7 +620,13 @@ static cudaError_t launch16_wftb(const AdcFilter16Args &a, int threads, size_t s
 // threads <= 512: two tiles per warp and iteration (TPI 2); more threads: one
 template <int W, bool FAST1>
 static cudaError_t launch16_wf(const AdcFilter16Args &a, int threads, size_t smem_bytes, cudaStream_t st, int b1) {
-  if (a.tmask) return launch16_wftb<W, FAST1, 1, 0, true>(a, 1024, smem_bytes, st);          // TI / visit
+  if (a.tmask) {          // TI / visit
+    if constexpr (FAST1 && W <= 2) {
+      if (b1 == 9) return launch16_wftb<W, true, 1, 9, true>(a, 1024, smem_bytes, st);
+      if (b1 == 10) return launch16_wftb<W, true, 1, 10, true>(a, 1024, smem_bytes, st);
+    }
+    return launch16_wftb<W, FAST1, 1, 0, true>(a, 1024, smem_bytes, st);
+  }
   if (threads <= 512) return launch16_wftb<W, FAST1, 2, 0>(a, threads, smem_bytes, st);
   if constexpr (FAST1 && W <= 2) {
     switch (b1) {          // uniform leading widths met in practice (budget / subspaces around 8 bits)

@@ -333,7 +333,8 @@ cudaError_t launch_refine(const float *xtrain, int64_t n, int D, const float *qu
                           const int32_t *in_labels, int refine_num, int k, int32_t *labels, float *dists,
                           cudaStream_t st);
 // TI / visit planning for the filter kernels (ti_plan.cu)
-cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clusters, int C, int segdims, const int64_t *rule_size,
+cudaError_t launch_transpose(const float *in, int rows, int cols, float *out, cudaStream_t st);
+cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clusters_t, int C, int segdims, const int64_t *rule_size,
                            float visit, int k, uint8_t *visited, int32_t *nearest, int32_t *perm, float *qperm, uint8_t *tmask,
                            cudaStream_t st);
 cudaError_t launch_tile_clusters(const int64_t *start, int C, int64_t n_rows, uint16_t *tile_cl, cudaStream_t st);

@@ -23,7 +23,7 @@ constexpr int kVisitWarps = 4;
 
 // dist[c] in shared memory (C floats per warp).  visited: [nq][C] bytes, nearest: [nq].
 __global__ void __launch_bounds__(kVisitWarps * 32) ti_visit_kernel(const float *__restrict__ q_proj, int nq, int D,
-                                                                    const float *__restrict__ clusters, int C, int segdims,
+                                                                    const float *__restrict__ clusters_t, int C, int segdims,
                                                                     const int64_t *__restrict__ rule_size, float visit, int k,
                                                                     uint8_t *__restrict__ visited, int32_t *__restrict__ nearest) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -36,10 +36,9 @@ __global__ void __launch_bounds__(kVisitWarps * 32) ti_visit_kernel(const float 
   // distances: the reference's generic fvec_L2sqr_ny path (utils/Math.hpp:8-35): sequential sum of (x - y)^2, then sqrt
   uint64_t best = 0xFFFFFFFFFFFFFFFFull;
   for (int c = lane; c < C; c += 32) {
-    const float *cc = clusters + (size_t)c * segdims;
     float acc = 0.f;
-    for (int j = 0; j < segdims; j++) {
-      const float d = __fsub_rn(qv[j], __ldg(cc + j));
+    for (int j = 0; j < segdims; j++) {          // clusters_t is dimension-major [segdims][C]: lanes read consecutive floats
+      const float d = __fsub_rn(qv[j], __ldg(clusters_t + (size_t)j * C + c));
       acc = __fadd_rn(acc, __fmul_rn(d, d));
     }
     const float dd = sqrtf(acc);
@@ -163,7 +162,7 @@ __global__ void tile_cluster_kernel(const int64_t *__restrict__ start, int C, in
   tile_cl[t] = (uint16_t)(c0 == c1 ? c0 : 0xFFFF);
 }
 
-cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clusters, int C, int segdims, const int64_t *rule_size,
+cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clusters_t, int C, int segdims, const int64_t *rule_size,
                            float visit, int k, uint8_t *visited, int32_t *nearest, int32_t *perm, float *qperm, uint8_t *tmask,
                            cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
@@ -172,7 +171,7 @@ cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clus
     static SmemOptIn optin;
     cudaError_t e = optin.ensure(ti_visit_kernel, smem);
     if (e != cudaSuccess) return e;
-    ti_visit_kernel<<<(nq + kVisitWarps - 1) / kVisitWarps, kVisitWarps * 32, smem, st>>>(q_proj, nq, D, clusters, C, segdims, rule_size,
+    ti_visit_kernel<<<(nq + kVisitWarps - 1) / kVisitWarps, kVisitWarps * 32, smem, st>>>(q_proj, nq, D, clusters_t, C, segdims, rule_size,
                                                                                         visit, k, visited, nearest);
   }
   {
@@ -193,4 +192,19 @@ cudaError_t launch_tile_clusters(const int64_t *start, int C, int64_t n_rows, ui
   return cudaGetLastError();
 }
 
+}  // namespace vaqgpu
+
+namespace vaqgpu {
+__global__ void transpose_kernel(const float *__restrict__ in, int rows, int cols, float *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+  out[(size_t)c * rows + r] = in[i];
+}
+cudaError_t launch_transpose(const float *in, int rows, int cols, float *out, cudaStream_t st) {
+  const int64_t n = (int64_t)rows * cols;
+  if (n <= 0) return cudaSuccess;
+  transpose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, rows, cols, out);
+  return cudaGetLastError();
+}
 }  // namespace vaqgpu

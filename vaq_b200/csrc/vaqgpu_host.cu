@@ -119,6 +119,7 @@ struct vaqgpu_index {
   int64_t *d_cl_start = nullptr, *d_cl_size = nullptr;
   int64_t *d_cl_rule = nullptr;    // cluster sizes the visiting rule counts (whole index; a row shard's own are smaller)
   int32_t *d_id_map = nullptr;
+  float *d_clusters_t = nullptr;   // the centres dimension-major [segdims][C] (coalesced reads of the visit kernel)
   uint16_t *d_tile_cl = nullptr;   // cluster of each 32-row tile (filter kernels); NULL when the ranges are not an ascending partition
 
   // refine
@@ -197,7 +198,8 @@ cudaError_t grow_codes(uint4 **codes, int64_t *cap_rows, int64_t n_rows, int W, 
 // (a TI search must never silently skip the new rows), and so does a failed vaqgpu_set_clusters.
 void clear_clusters(vaqgpu_index *h) {
   cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_id_map);
-  cudaFree(h->d_cl_rule); cudaFree(h->d_tile_cl);
+  cudaFree(h->d_cl_rule); cudaFree(h->d_tile_cl); cudaFree(h->d_clusters_t);
+  h->d_clusters_t = nullptr;
   h->d_clusters = nullptr; h->d_cl_start = h->d_cl_size = h->d_cl_rule = nullptr; h->d_id_map = nullptr; h->d_tile_cl = nullptr;
   h->C = 0; h->segdims = 0;
 }
@@ -512,7 +514,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       const float *qp = d_qproj + (size_t)q0 * h->D;
       if (ti) {
         // which clusters each query visits, queries grouped into tiles by nearest cluster, per-(tile, cluster) masks
-        CU(launch_ti_plan(qp, qb, h->D, h->d_clusters, h->C, h->segdims, h->d_cl_rule ? h->d_cl_rule : h->d_cl_size, h->visit, k,
+        CU(launch_ti_plan(qp, qb, h->D, h->d_clusters_t, h->C, h->segdims, h->d_cl_rule ? h->d_cl_rule : h->d_cl_size, h->visit, k,
                           (uint8_t *)h->w_vis.p, (int32_t *)h->w_near.p, (int32_t *)h->w_perm.p, (float *)h->w_qperm.p,
                           (uint8_t *)h->w_tmask.p, st));
         qp = (const float *)h->w_qperm.p;          // the batch in tile order
@@ -800,7 +802,7 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_centroids); cudaFree(h->d_cent_rmax); cudaFree(h->d_eig); cudaFree(h->d_bits); cudaFree(h->d_ent_off); cudaFree(h->d_cent_off);
-  cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_cl_rule); cudaFree(h->d_tile_cl);
+  cudaFree(h->d_codes); cudaFree(h->d_clusters); cudaFree(h->d_cl_start); cudaFree(h->d_cl_size); cudaFree(h->d_cl_rule); cudaFree(h->d_tile_cl); cudaFree(h->d_clusters_t);
   cudaFree(h->d_id_map); cudaFree(h->d_raw);
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_bounds);
@@ -1048,6 +1050,8 @@ int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t s
     const int64_t n_tiles = (h->n_rows + kTileRows - 1) / kTileRows;
     e = cudaMalloc(&h->d_tile_cl, (size_t)std::max<int64_t>(1, n_tiles) * sizeof(uint16_t));
     if (e == cudaSuccess) e = launch_tile_clusters(h->d_cl_start, C, h->n_rows, h->d_tile_cl, h->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_clusters_t, (size_t)C * segdims * sizeof(float));
+    if (e == cudaSuccess) e = launch_transpose(h->d_clusters, C, segdims, h->d_clusters_t, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   }
   if (e != cudaSuccess) {
@@ -1117,6 +1121,10 @@ int vaqgpu_cluster_ti(vaqgpu_t *h, int32_t C, int32_t n_segments, int32_t iters)
     CT(cudaGetLastError());
   }
   CT(launch_tile_clusters(start, C, n, tile_cl, st));
+  float *centres_t = nullptr;
+  CT(cudaMalloc(&centres_t, (size_t)C * seg * h->L * sizeof(float)));
+  h->d_clusters_t = centres_t;          // owned by the handle from here on (clear_clusters frees it)
+  CT(launch_transpose(centres, C, seg * h->L, centres_t, st));
   CT(cudaStreamSynchronize(st));
 #undef CT
   cudaFree(h->d_codes);
