@@ -25,6 +25,10 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -58,6 +62,139 @@ using bitvectors = std::vector<bitv>;      // BitVector.hpp:19
 #ifdef VAQGPU_HAVE_EIGEN
 using RowMatrixXf = Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>;      // utils/Types.hpp:14-16
 #endif
+
+// ---- on-disk formats of the reference (bitvecengine/utils/IO.hpp), so a C++ caller can load what the reference wrote ----
+namespace io {
+
+inline std::vector<unsigned char> slurp(const std::string &path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot open " + path);
+  return std::vector<unsigned char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+// fvecs / ivecs / bvecs: per record an int32 dimension followed by that many float32 / int32 / uint8
+// (readFVecsFromExternal IO.hpp:126-161, readIVecsFromExternal :334-361, readBVecsFromExternal :198-233 — the byte
+// reader fills a float matrix, as here).  Returns row-major [rows x dim].
+template <class T, class Out>
+inline std::vector<Out> readVecs(const std::string &path, int &dim, long &rows, long max_rows = -1) {
+  const std::vector<unsigned char> raw = slurp(path);
+  if (raw.size() < 4) { dim = 0; rows = 0; return {}; }
+  int32_t d; std::memcpy(&d, raw.data(), 4);
+  const size_t rec = 4 + (size_t)d * sizeof(T);
+  if (d <= 0 || raw.size() % rec) throw std::runtime_error(path + ": not a well-formed vecs file");
+  dim = d; rows = (long)(raw.size() / rec);
+  if (max_rows >= 0 && rows > max_rows) rows = max_rows;
+  std::vector<Out> out((size_t)rows * d);
+  for (long r = 0; r < rows; r++) {
+    const unsigned char *p = raw.data() + (size_t)r * rec + 4;
+    for (int j = 0; j < d; j++) { T v; std::memcpy(&v, p + (size_t)j * sizeof(T), sizeof(T)); out[(size_t)r * d + j] = (Out)v; }
+  }
+  return out;
+}
+inline std::vector<float> readFVecs(const std::string &path, int &dim, long &rows, long max_rows = -1) { return readVecs<float, float>(path, dim, rows, max_rows); }
+inline std::vector<int> readIVecs(const std::string &path, int &dim, long &rows, long max_rows = -1) { return readVecs<int32_t, int>(path, dim, rows, max_rows); }
+inline std::vector<float> readBVecs(const std::string &path, int &dim, long &rows, long max_rows = -1) { return readVecs<uint8_t, float>(path, dim, rows, max_rows); }
+
+// saveCentroids / loadCentroids (IO.hpp:736-754, 522-549): size_t n; per subspace size_t rows, cols, float32[rows*cols].
+// Returns the concatenated row-major blocks; K[s] = rows of block s, L = cols.
+inline std::vector<float> loadCentroids(const std::string &path, std::vector<int> &K, int &L) {
+  const std::vector<unsigned char> raw = slurp(path);
+  size_t off = 0;
+  auto rd64 = [&]() { if (off + 8 > raw.size()) throw std::runtime_error(path + ": truncated"); uint64_t v; std::memcpy(&v, raw.data() + off, 8); off += 8; return v; };
+  const uint64_t n = rd64();
+  std::vector<float> out;
+  K.clear(); L = 0;
+  for (uint64_t s = 0; s < n; s++) {
+    const uint64_t rows = rd64(), cols = rd64();
+    if (off + rows * cols * 4 > raw.size()) throw std::runtime_error(path + ": truncated");
+    const size_t at = out.size();
+    out.resize(at + rows * cols);
+    std::memcpy(out.data() + at, raw.data() + off, rows * cols * 4);
+    off += rows * cols * 4;
+    K.push_back((int)rows); L = (int)cols;
+  }
+  return out;
+}
+inline void saveCentroids(const std::string &path, const float *cent, const std::vector<int> &K, int L) {
+  std::ofstream f(path, std::ios::binary);
+  const uint64_t n = K.size();
+  f.write((const char *)&n, 8);
+  size_t off = 0;
+  for (int k : K) {
+    const uint64_t rows = (uint64_t)k, cols = (uint64_t)L;
+    f.write((const char *)&rows, 8); f.write((const char *)&cols, 8);
+    f.write((const char *)(cent + off), (std::streamsize)(rows * cols * 4));
+    off += rows * cols;
+  }
+}
+// saveCodebook / loadCodebook (IO.hpp:757-772, 552-571): size_t rows, cols, uint16[rows*cols] row-major (mCodebook)
+inline std::vector<uint16_t> loadCodebook(const std::string &path, size_t &rows, size_t &cols) {
+  const std::vector<unsigned char> raw = slurp(path);
+  if (raw.size() < 16) throw std::runtime_error(path + ": truncated");
+  uint64_t r, c; std::memcpy(&r, raw.data(), 8); std::memcpy(&c, raw.data() + 8, 8);
+  if (raw.size() < 16 + r * c * 2) throw std::runtime_error(path + ": truncated codebook");
+  std::vector<uint16_t> out((size_t)(r * c));
+  std::memcpy(out.data(), raw.data() + 16, (size_t)(r * c * 2));
+  rows = (size_t)r; cols = (size_t)c;
+  return out;
+}
+inline void saveCodebook(const std::string &path, const uint16_t *codes, size_t rows, size_t cols) {
+  std::ofstream f(path, std::ios::binary);
+  const uint64_t r = rows, c = cols;
+  f.write((const char *)&r, 8); f.write((const char *)&c, 8);
+  f.write((const char *)codes, (std::streamsize)(rows * cols * 2));
+}
+
+// actualBitVLen / createBitV (BitVector.hpp:36-76).  The scalar overload shifts a 64-bit value by multiples of 64
+// for N > 64 (undefined in C++; x86-64 takes the count modulo 64): restated as the compiled reference behaves.
+inline int actualBitVLen(int N) { return (N + 63) / 64; }
+inline bitv createBitV(int N, uint64_t raw) {
+  bitv v((size_t)actualBitVLen(N), 0);
+  const int len = (int)v.size();
+  if (N <= 64) { v[0] = raw; return v; }
+  for (int i = 0; i < len - 1; i++) v[(size_t)i] = raw;
+  const int rest = N - (len - 1) * 64;
+  v[(size_t)len - 1] = rest >= 64 ? raw : (raw & ((1ull << rest) - 1ull));
+  return v;
+}
+// bit-vector CSV: readFromExternal(filepath, bitvectors&, cols, delim) (IO.hpp:363-397) / writeToExternal (:681-704).
+// Column c is bit 63 - (c % 64) of word c / 64.  With cols % 64 != 0 the reference shifts the last, partial word once
+// too often (its first column falls out of the register); reproduced, as in vaq_b200/io.py.
+inline void readBitVectorsCSV(const std::string &path, bitvectors &bv, int cols, char delim = ',') {
+  std::ifstream in(path);
+  std::string line, bit;
+  while (std::getline(in, line)) {
+    if (line.empty()) break;
+    bitv v((size_t)actualBitVLen(cols), 0);
+    std::stringstream ss(line);
+    int counter = 0;
+    uint64_t acc = 0;
+    while (std::getline(ss, bit, delim) && counter < cols) {
+      acc |= (uint64_t)std::stoi(bit);
+      counter++;
+      if (counter % 64 == 0) { v[(size_t)(counter / 64) - 1] = acc; acc = 0; }
+      else acc <<= 1;
+    }
+    if (counter % 64 != 0) v[(size_t)(counter / 64)] = acc << (64 - (counter % 64));
+    bv.push_back(v);
+  }
+}
+inline void writeBitVectorsCSV(const std::string &path, const bitvectors &bv, int N) {
+  std::ofstream out(path);
+  for (const bitv &row : bv) {
+    for (int i = 0; i < (int)row.size(); i++) {
+      const int maxBin = ((i + 1) * 64 <= N) ? 64 : (N % 64);
+      for (int b = 0; b < maxBin; b++) {
+        out << (int)((row[(size_t)i] >> (63 - b)) & 1u);
+        if (b != maxBin - 1) out << ',';
+      }
+      if (i != (int)row.size() - 1) out << ',';
+    }
+    out << '\n';
+  }
+}
+
+}  // namespace io
 
 inline void check(int rc) {
   if (rc != VAQGPU_OK) throw std::runtime_error(std::string("vaqgpu: ") + vaqgpu_last_error());
@@ -115,6 +252,26 @@ class VAQ {
     d.bits = bitsAlloc; d.centroids = centroidsPerSubs; d.eig_real = eigReal;
     check(vaqgpu_create(&d, device_, &h_));
     has_eig_ = eigReal != nullptr;
+  }
+
+  // An index the reference saved with saveCentroids + saveCodebook (examples/demo_vaq.cpp:127-140, utils/IO.hpp:736-772):
+  // bits follow from the centroid counts; eigReal [D x D] when queries arrive raw.
+  void loadIndexFiles(const std::string &centroidsPath, const std::string &codebookPath, const float *eigReal = nullptr) {
+    std::vector<int> K;
+    int L = 0;
+    const std::vector<float> cent = io::loadCentroids(centroidsPath, K, L);
+    std::vector<int> bits;
+    for (int k : K) {
+      int b = 0;
+      while ((1 << b) < k) b++;
+      if ((1 << b) != k) throw std::runtime_error("loadIndexFiles: centroid count is not a power of two");
+      bits.push_back(b);
+    }
+    loadModel(L, (int)K.size(), bits.data(), cent.data(), eigReal);
+    size_t rows = 0, cols = 0;
+    const std::vector<uint16_t> codes = io::loadCodebook(codebookPath, rows, cols);
+    if ((int)cols != mHighestSubs) throw std::runtime_error("loadIndexFiles: codebook columns != subspaces");
+    setCodebook(codes.data(), (int64_t)rows);
   }
 
   // mCodebook (VAQ.hpp:72): row-major [n x mHighestSubs] uint16, as VAQ::encode left it on the host

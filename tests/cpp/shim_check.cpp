@@ -5,6 +5,7 @@
 // exit codes: 0 ok, 3 no usable GPU (std::runtime_error from the shim), 4 known-answer mismatch
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "vaq_gpu.hpp"
@@ -16,9 +17,38 @@ static std::vector<T> rd(FILE *f, size_t n) {
   return v;
 }
 
+// shim_check files <centroids.bin> <codebook.bin> <queries.fvecs> <k> <out.bin>: an index written in the reference's
+// on-disk formats (utils/IO.hpp:736-772) + fvecs queries, loaded by the shim's own readers
+static int files_mode(char **argv) {
+  vaqgpu::VAQ vaq;
+  vaq.parseMethodString("VAQ64m8min5max10var1,EA");
+  vaq.loadIndexFiles(argv[2], argv[3]);
+  int dim = 0; long nq = 0;
+  std::vector<float> q = vaqgpu::io::readFVecs(argv[4], dim, nq);
+  const int k = atoi(argv[5]);
+  vaqgpu::LabelDistVecF ans = vaq.search(q.data(), (int)nq, k);
+  // bit-vector CSV helpers round-trip
+  vaqgpu::bitvectors bv = {vaqgpu::io::createBitV(128, 0x8000000000000001ull), {0x0123456789ABCDEFull, 0xFEDCBA9876543210ull}};
+  const std::string csv = std::string(argv[6]) + ".csv";
+  vaqgpu::io::writeBitVectorsCSV(csv, bv, 128);
+  vaqgpu::bitvectors back;
+  vaqgpu::io::readBitVectorsCSV(csv, back, 128);
+  if (back != bv) { fprintf(stderr, "bit-vector CSV round trip failed\n"); return 4; }
+  FILE *o = fopen(argv[6], "wb");
+  fwrite(ans.labels.data(), sizeof(int), ans.labels.size(), o);
+  fwrite(ans.distances.data(), sizeof(float), ans.distances.size(), o);
+  fclose(o);
+  printf("shim_check files ok\n");
+  return 0;
+}
+
 int main(int argc, char **argv) {
-  if (argc < 3) { fprintf(stderr, "usage: shim_check in.bin out.bin\n"); return 2; }
+  if (argc < 3) { fprintf(stderr, "usage: shim_check in.bin out.bin | shim_check files centroids.bin codebook.bin queries.fvecs k out.bin\n"); return 2; }
   try {
+    if (std::string(argv[1]) == "files") {
+      if (argc < 7) return 2;
+      return files_mode(argv);
+    }
     FILE *f = fopen(argv[1], "rb");
     if (!f) { perror("open"); return 2; }
     auto hdr = rd<int32_t>(f, 6);            // L, M, nq, k, has_eig, n

@@ -119,3 +119,26 @@ def test_demo_query_phase_compiles_unchanged(tmp_path):
     rl, rd = orc.Port().refine(g["Qraw"], l40, g["X"], k)
     np.testing.assert_allclose(dis2, rd, rtol=1e-4)
     assert (lab2 == rl).mean() > 0.95
+
+
+@pytest.mark.gpu
+def test_shim_loads_an_index_in_the_reference_file_formats(tmp_path):
+    """saveCentroids / saveCodebook files (byte-identical to the reference's writers, tests/test_io_formats.py) + fvecs
+    queries, read by the C++ shim's own loaders (vaqgpu::io, VAQ::loadIndexFiles) and searched."""
+    from vaq_b200 import io as vio
+    exe = build_binary(tmp_path)
+    g = load_golden("vaq_small_a")
+    m, _ = golden_model(g)
+    vio.save_centroids(tmp_path / "c.bin", m.centroids)
+    vio.save_codebook(tmp_path / "cb.bin", g["codes"])
+    vio.write_fvecs(tmp_path / "q.fvecs", g["Q"])
+    k = int(g["k"])
+    r = subprocess.run([str(exe), "files", str(tmp_path / "c.bin"), str(tmp_path / "cb.bin"), str(tmp_path / "q.fvecs"), str(k),
+                        str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    nq = g["Q"].shape[0]
+    raw = np.fromfile(tmp_path / "out.bin", np.uint8)
+    n = nq * k * 4
+    lab = raw[:n].view(np.int32).reshape(nq, k); dis = raw[n:2 * n].view(np.float32).reshape(nq, k)
+    want_lab, want_dis = orc.Port().search_lex(m, g["codes"], g["Q"], k)
+    assert np.array_equal(lab, want_lab) and bitwise_equal(dis, want_dis)

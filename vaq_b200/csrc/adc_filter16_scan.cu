@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   const int spl = (int)min((grid_chunks >= 32u && grid_qtiles <= 2u) ? 1u : 4u, rows_here / (blockDim.x * 4u));
   int unbounded = 0;
   if (tid < T8 && q0 + tid < a.nq) unbounded = thr_f[tid] == 0xFFFFFFFFu;
-  if (!TI && a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64 && __syncthreads_or(unbounded)) {
+  if (a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64 && __syncthreads_or(unbounded)) {
     const uint32_t step = rows_here / (blockDim.x * (uint32_t)spl);
     __half2 best[4];
     best[0] = best[1] = best[2] = best[3] = as_h2(0x7C007C00u);        // +inf
@@ -289,6 +289,15 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
           const uint4 v = lds128(s_base + (a.lay.foff[f] + code) * (T8 * 2));
           acc[0] = __hadd2(acc[0], as_h2(v.x)); acc[1] = __hadd2(acc[1], as_h2(v.y));
           acc[2] = __hadd2(acc[2], as_h2(v.z)); acc[3] = __hadd2(acc[3], as_h2(v.w));
+        }
+      }
+      if constexpr (TI) {
+        // a sample row only bounds the queries that visit its cluster: the others see +inf for it
+        const uint32_t cm = smask[cluster_of_row(a.cl_start, a.C, row)];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t inf2 = (((cm >> (2 * i)) & 1u) ? 0u : 0x7C00u) | (((cm >> (2 * i + 1)) & 1u) ? 0u : 0x7C000000u);
+          acc[i] = __hmax2(acc[i], as_h2(inf2));
         }
       }
 #pragma unroll

@@ -298,7 +298,8 @@ cudaError_t launch_unpack_codes(const uint4 *packed, int64_t row0, int64_t n, co
                                 const uint32_t *rowid, int64_t srow_lo, int64_t srow_hi, cudaStream_t st);
 // conflict-aware row order (layout.cu)
 cudaError_t launch_layout(uint4 *codes, int64_t row_lo, int64_t n_rows, const ScanLayout &lay, uint32_t *rowid, uint16_t *src,
-                          uint4 *scratch, int scratch_ctas, bool restore, cudaStream_t st);
+                          uint4 *scratch, int scratch_ctas, const int64_t *win_tab, int64_t n_windows, cudaStream_t st);
+cudaError_t launch_layout_restore(const uint4 *tmp_copy, uint4 *codes, int W, const uint32_t *rowid, int64_t n, cudaStream_t st);
 size_t layout_scratch_bytes(int W, int ctas);
 cudaError_t launch_iota_u32(uint32_t *p, int64_t lo, int64_t hi, cudaStream_t st);
 cudaError_t launch_encode(const float *x_proj, int64_t n, const float *centroids, const LutPlan &plan,

@@ -51,15 +51,25 @@ __device__ __forceinline__ uint32_t key_onehot(uint32_t key, int nf) {
 
 // One warp per window.  src[window * kLayoutWin + slot] = index (inside the window, current storage order) of the
 // row that moves to `slot`.  Slots 8g .. 8g+7 form one quarter-warp of the scan.
+// Windows: win_tab == NULL -> window w covers rows [row_lo + w * kLayoutWin, ... + kLayoutWin) clipped to n_rows;
+// otherwise win_tab[w] = (first row, row count <= kLayoutWin) — TI indexes, whose windows may not cross clusters.
+__device__ __forceinline__ void window_of(const int64_t *__restrict__ win_tab, int64_t win, int64_t row_lo, int64_t n_rows, int64_t &base, int &n) {
+  if (win_tab) { base = win_tab[2 * win]; n = (int)win_tab[2 * win + 1]; }
+  else { base = row_lo + win * kLayoutWin; n = (int)min((int64_t)kLayoutWin, n_rows - base); }
+}
+
 __global__ void __launch_bounds__(kPlanWarps * 32) layout_plan_kernel(const uint4 *__restrict__ codes, int W, int64_t row_lo,
                                                                       int64_t n_rows, const __grid_constant__ ScanLayout lay,
-                                                                      uint16_t *__restrict__ src) {
+                                                                      uint16_t *__restrict__ src, const int64_t *__restrict__ win_tab,
+                                                                      int64_t n_windows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t win = (int64_t)blockIdx.x * kPlanWarps + warp;
-  const int64_t base = row_lo + win * kLayoutWin;
-  if (base >= n_rows) return;
-  const int n = (int)min((int64_t)kLayoutWin, n_rows - base);
+  if (win >= n_windows) return;
+  int64_t base;
+  int n;
+  window_of(win_tab, win, row_lo, n_rows, base, n);
+  if (n <= 0) return;
   uint16_t *keys = reinterpret_cast<uint16_t *>(smem_raw) + (size_t)warp * 2 * kLayoutWin;      // [n] residue key per row
   uint16_t *bk = keys + kLayoutWin;                                                              // [8 buckets] row lists
   const int nf = min(4, lay.M);
@@ -149,38 +159,50 @@ __global__ void __launch_bounds__(kPlanWarps * 32) layout_plan_kernel(const uint
   }
 }
 
-// Inverse of the current order of a window: src[orig - base] = slot, for restoring the arrival order.
-__global__ void layout_inverse_kernel(const uint32_t *__restrict__ rowid, int64_t row_lo, int64_t n_rows, uint16_t *__restrict__ src) {
-  const int64_t s = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_rows) return;
-  const int64_t base = row_lo + ((s - row_lo) / kLayoutWin) * kLayoutWin;
-  src[(base - row_lo) + (rowid[s] - base)] = (uint16_t)(s - base);
-}
-
-// new[slot] = old[src[slot]] for the rows (all W words) and the row ids of each window.  A CTA stages its window in a
-// private scratch slot (global memory, L2-resident), then gathers from it.  Persistent CTAs.
+// new[slot] = old[src[slot]] for the rows (all W words) and the row ids of each window.  A CTA stages its window row by
+// row in a private scratch slot (global memory, L2-resident), then gathers from it.  Persistent CTAs.
 __global__ void __launch_bounds__(256) layout_apply_kernel(uint4 *__restrict__ codes, int W, int64_t row_lo, int64_t n_rows,
                                                             const uint16_t *__restrict__ src, uint32_t *__restrict__ rowid,
-                                                            uint4 *__restrict__ scratch, int64_t n_windows) {
+                                                            uint4 *__restrict__ scratch, const int64_t *__restrict__ win_tab,
+                                                            int64_t n_windows) {
   uint4 *mine = scratch + (size_t)blockIdx.x * ((size_t)kLayoutWin * W + kLayoutWin / 4);
   uint32_t *ids = reinterpret_cast<uint32_t *>(mine + (size_t)kLayoutWin * W);
   for (int64_t win = blockIdx.x; win < n_windows; win += gridDim.x) {
-    const int64_t base = row_lo + win * kLayoutWin;       // a multiple of kLayoutWin, hence of the tile size
-    const int n = (int)min((int64_t)kLayoutWin, n_rows - base);
-    const int tiles = (n + kTileRows - 1) / kTileRows;
-    uint4 *wcodes = codes + (size_t)(base >> 5) * W * kTileRows;
-    for (int i = threadIdx.x; i < tiles * W * kTileRows; i += blockDim.x) mine[i] = wcodes[i];
+    int64_t base;
+    int n;
+    window_of(win_tab, win, row_lo, n_rows, base, n);
+    for (int i = threadIdx.x; i < n * W; i += blockDim.x) {
+      const int r = i / W, j = i - r * W;
+      const int64_t row = base + r;
+      mine[i] = codes[((size_t)(row >> 5) * W + j) * kTileRows + (row & 31)];
+    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) ids[i] = rowid[base + i];
     __threadfence_block();
     __syncthreads();
     for (int i = threadIdx.x; i < n * W; i += blockDim.x) {
       const int slot = i / W, j = i - slot * W;
-      const int s = src[(base - row_lo) + slot];
-      wcodes[((size_t)(slot >> 5) * W + j) * kTileRows + (slot & 31)] = mine[((size_t)(s >> 5) * W + j) * kTileRows + (s & 31)];
+      const int64_t row = base + slot;
+      codes[((size_t)(row >> 5) * W + j) * kTileRows + (row & 31)] = mine[(size_t)src[(base - row_lo) + slot] * W + j];
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) rowid[base + i] = ids[src[(base - row_lo) + i]];
     __syncthreads();
   }
+}
+
+// Back to the order the row ids describe: dst[rowid[s]] = src[s] for every row s < n (rowid a permutation of [0, n)).
+__global__ void layout_scatter_kernel(const uint4 *__restrict__ srcm, uint4 *__restrict__ dst, int W, const uint32_t *__restrict__ rowid, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * W) return;
+  const int64_t s = i / W;
+  const int j = (int)(i - s * W);
+  const int64_t t = rowid[s];
+  dst[((size_t)(t >> 5) * W + j) * kTileRows + (t & 31)] = srcm[((size_t)(s >> 5) * W + j) * kTileRows + (s & 31)];
+}
+
+cudaError_t launch_layout_restore(const uint4 *tmp_copy, uint4 *codes, int W, const uint32_t *rowid, int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  layout_scatter_kernel<<<(unsigned)((n * W + 255) / 256), 256, 0, st>>>(tmp_copy, codes, W, rowid, n);
+  return cudaGetLastError();
 }
 
 __global__ void iota_u32_kernel(uint32_t *__restrict__ p, int64_t lo, int64_t hi) {
@@ -196,25 +218,21 @@ cudaError_t launch_iota_u32(uint32_t *p, int64_t lo, int64_t hi, cudaStream_t st
 
 size_t layout_scratch_bytes(int W, int ctas) { return (size_t)ctas * ((size_t)kLayoutWin * W + kLayoutWin / 4) * sizeof(uint4); }
 
-// Re-orders the windows that cover rows [row_lo, n_rows) (row_lo a multiple of kLayoutWin).  restore = true puts the
-// rows back into arrival order instead (rowid becomes the identity).  src: (n_rows - row_lo) uint16 of workspace.
+// Re-orders the given windows (win_tab NULL: the aligned windows that cover rows [row_lo, n_rows), row_lo a multiple of
+// kLayoutWin).  src: one uint16 per row of [row_lo, n_rows) of workspace.
 cudaError_t launch_layout(uint4 *codes, int64_t row_lo, int64_t n_rows, const ScanLayout &lay, uint32_t *rowid, uint16_t *src,
-                          uint4 *scratch, int scratch_ctas, bool restore, cudaStream_t st) {
-  if (n_rows <= row_lo) return cudaSuccess;
-  const int64_t n_windows = (n_rows - row_lo + kLayoutWin - 1) / kLayoutWin;
-  if (restore) {
-    layout_inverse_kernel<<<(unsigned)((n_rows - row_lo + 255) / 256), 256, 0, st>>>(rowid, row_lo, n_rows, src);
-  } else {
-    const size_t smem = (size_t)kPlanWarps * 2 * kLayoutWin * sizeof(uint16_t);
-    static SmemOptIn optin;
-    cudaError_t e = optin.ensure(layout_plan_kernel, smem);
-    if (e != cudaSuccess) return e;
-    layout_plan_kernel<<<(unsigned)((n_windows + kPlanWarps - 1) / kPlanWarps), kPlanWarps * 32, smem, st>>>(codes, lay.W, row_lo, n_rows, lay, src);
-  }
-  cudaError_t e = cudaGetLastError();
+                          uint4 *scratch, int scratch_ctas, const int64_t *win_tab, int64_t n_windows, cudaStream_t st) {
+  if (n_rows <= row_lo || n_windows <= 0) return cudaSuccess;
+  const size_t smem = (size_t)kPlanWarps * 2 * kLayoutWin * sizeof(uint16_t);
+  static SmemOptIn optin;
+  cudaError_t e = optin.ensure(layout_plan_kernel, smem);
+  if (e != cudaSuccess) return e;
+  layout_plan_kernel<<<(unsigned)((n_windows + kPlanWarps - 1) / kPlanWarps), kPlanWarps * 32, smem, st>>>(codes, lay.W, row_lo, n_rows, lay, src,
+                                                                                                      win_tab, n_windows);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int ctas = (int)std::min<int64_t>(n_windows, scratch_ctas);
-  layout_apply_kernel<<<ctas, 256, 0, st>>>(codes, lay.W, row_lo, n_rows, src, rowid, scratch, n_windows);
+  layout_apply_kernel<<<ctas, 256, 0, st>>>(codes, lay.W, row_lo, n_rows, src, rowid, scratch, win_tab, n_windows);
   return cudaGetLastError();
 }
 

@@ -136,6 +136,8 @@ struct vaqgpu_index {
   uint32_t *d_rowid = nullptr;
   int64_t rowid_cap = 0, rowid_n = 0, opt_n = 0;
   float layout_ms = 0.f;
+  bool cluster_windows = false;                  // the re-ordering windows follow the TI clusters (not aligned 4096-row blocks)
+  std::vector<int64_t> h_cl_start, h_cl_size;    // host copies of the TI cluster ranges
 
   // cross-shard bound exchange (vaqgpu_bounds_*): two halves of bounds_cap entries, used alternately by
   // successive searches; the half the NEXT search will use is reset while this one runs
@@ -357,9 +359,10 @@ int ensure_rowid(vaqgpu_index *h, cudaStream_t st) {
 }
 
 // Re-orders the windows that hold rows added since the last call (the filter kernels call this before scanning).
-// Skipped while TI clusters are set: their row ranges are defined on the arrival order.
+// With TI clusters set the windows are pieces of the clusters (<= kLayoutWin rows each), so every cluster keeps its
+// row range and the cluster-of-tile map stays valid.
 int ensure_layout(vaqgpu_index *h, cudaStream_t st) {
-  if (h->C > 0 || h->n_rows <= h->opt_n || tune_knob("layout", 1) == 0) return ensure_rowid(h, st);
+  if (h->n_rows <= h->opt_n || tune_knob("layout", 1) == 0) return ensure_rowid(h, st);
   if (!h->d_rowid) {
     const int64_t cap = std::max(h->cap_rows, h->n_rows);
     CU(cudaMalloc(&h->d_rowid, (size_t)cap * sizeof(uint32_t)));
@@ -367,15 +370,35 @@ int ensure_layout(vaqgpu_index *h, cudaStream_t st) {
   }
   int rc = ensure_rowid(h, st);
   if (rc) return rc;
-  const int64_t row_lo = (h->opt_n / kLayoutWin) * kLayoutWin;          // a partially filled window is planned again
-  const int64_t n_windows = (h->n_rows - row_lo + kLayoutWin - 1) / kLayoutWin;
-  const int ctas = (int)std::min<int64_t>(n_windows, 2 * h->num_sms);
+  int64_t row_lo = (h->opt_n / kLayoutWin) * kLayoutWin;          // a partially filled window is planned again
+  int64_t n_windows = (h->n_rows - row_lo + kLayoutWin - 1) / kLayoutWin;
+  const int64_t *d_win = nullptr;
+  DevBuf w_win;
+  if (h->C > 0) {
+    std::vector<int64_t> tab;
+    for (int c = 0; c < h->C; c++)
+      for (int64_t off = 0; off < h->h_cl_size[c]; off += kLayoutWin) {
+        tab.push_back(h->h_cl_start[c] + off);
+        tab.push_back(std::min<int64_t>(kLayoutWin, h->h_cl_size[c] - off));
+      }
+    row_lo = 0;
+    n_windows = (int64_t)tab.size() / 2;
+    if (n_windows > 0) {
+      CU(w_win.ensure(tab.size() * sizeof(int64_t)));
+      CU(cudaMemcpyAsync(w_win.p, tab.data(), tab.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));
+      d_win = (const int64_t *)w_win.p;
+    }
+    h->cluster_windows = true;
+  }
+  const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(n_windows, 2 * h->num_sms));
   CU(h->w_lsrc.ensure((size_t)(h->n_rows - row_lo) * sizeof(uint16_t)));
   CU(h->w_lscratch.ensure(layout_scratch_bytes(h->lay.W, ctas)));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   CU(cudaEventRecord(e0, st));
-  CU(launch_layout(h->d_codes, row_lo, h->n_rows, h->lay, h->d_rowid, (uint16_t *)h->w_lsrc.p, (uint4 *)h->w_lscratch.p, ctas, false, st));
+  CU(launch_layout(h->d_codes, row_lo, h->n_rows, h->lay, h->d_rowid, (uint16_t *)h->w_lsrc.p, (uint4 *)h->w_lscratch.p, ctas, d_win,
+                   n_windows, st));
   CU(cudaEventRecord(e1, st));
   CU(cudaEventSynchronize(e1));
   float ms = 0.f;
@@ -383,24 +406,37 @@ int ensure_layout(vaqgpu_index *h, cudaStream_t st) {
   h->layout_ms += ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   h->w_lscratch.release();
+  w_win.release();
   h->opt_n = h->n_rows;
   return VAQGPU_OK;
 }
 
-// Back to the arrival order (TI cluster ranges are defined on it).
+// Back to the arrival order (TI cluster ranges are defined on it): every row returns to the position its id names.
 int restore_layout(vaqgpu_index *h, cudaStream_t st) {
   if (!h->d_rowid || h->opt_n == 0) return VAQGPU_OK;
   int rc = ensure_rowid(h, st);
   if (rc) return rc;
-  const int64_t n_windows = (h->opt_n + kLayoutWin - 1) / kLayoutWin;
-  const int ctas = (int)std::min<int64_t>(n_windows, 2 * h->num_sms);
-  CU(h->w_lsrc.ensure((size_t)h->opt_n * sizeof(uint16_t)));
-  CU(h->w_lscratch.ensure(layout_scratch_bytes(h->lay.W, ctas)));
-  CU(launch_layout(h->d_codes, 0, h->opt_n, h->lay, h->d_rowid, (uint16_t *)h->w_lsrc.p, (uint4 *)h->w_lscratch.p, ctas, true, st));
-  CU(cudaStreamSynchronize(st));
-  h->w_lscratch.release();
+  const int64_t tiles = (h->n_rows + kTileRows - 1) / kTileRows;
+  const size_t bytes = (size_t)tiles * kTileRows * h->lay.W * sizeof(uint4);
+  uint4 *tmp = nullptr;
+  CU(cudaMalloc(&tmp, bytes));
+  cudaError_t e = cudaMemcpyAsync(tmp, h->d_codes, bytes, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = launch_layout_restore(tmp, h->d_codes, h->lay.W, h->d_rowid, h->n_rows, st);
+  if (e == cudaSuccess) e = launch_iota_u32(h->d_rowid, 0, h->n_rows, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(VAQGPU_ECUDA, "restore_layout: %s", cudaGetErrorString(e));
   h->opt_n = 0;
+  h->cluster_windows = false;
   return VAQGPU_OK;
+}
+
+// Appending rows (or replacing the clusters) ends the current TI state: rows go back to their cluster-grouped order first.
+int drop_clusters(vaqgpu_index *h) {
+  if (!h->C) return VAQGPU_OK;
+  int rc = restore_layout(h, h->stream);
+  clear_clusters(h);
+  return rc;
 }
 
 // The whole device-side search; exactly one of (d_labels,d_dists) / d_keys is the output.
@@ -539,7 +575,6 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       if (ti) {
         a.tile_cl = h->d_tile_cl; a.cl_start = h->d_cl_start; a.tmask = (const uint8_t *)h->w_tmask.p; a.C = h->C;
         a.qmap = (const int32_t *)h->w_perm.p;
-        a.seed = 0;          // sample rows would have to be rows the query visits
       }
       a.chunks_fast = tune_knob("chunks_fast", 0);
       // a code matrix far larger than L2 streams from HBM: keep more of it in flight than the register prefetch holds
@@ -849,7 +884,10 @@ int vaqgpu_add_codes_u16(vaqgpu_t *h, const uint16_t *codes, int64_t n) {
   if (n == 0) return VAQGPU_OK;
   if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index (labels are int32, utils/Types.hpp:100)");
   DeviceGuard g(h->device);
-  if (h->C) clear_clusters(h);
+  {
+    int rc_ = drop_clusters(h);
+    if (rc_) return rc_;
+  }
   CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
   const int64_t chunk = std::min<int64_t>(n, kStageRows);
   CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
@@ -869,7 +907,10 @@ int vaqgpu_encode_add(vaqgpu_t *h, const float *x_proj, int64_t n) {
   if (n == 0) return VAQGPU_OK;
   if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index");
   DeviceGuard g(h->device);
-  if (h->C) clear_clusters(h);
+  {
+    int rc_ = drop_clusters(h);
+    if (rc_) return rc_;
+  }
   CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
   const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t)(256ull << 20) / (h->D * 4)));
   CU(h->w_stage.ensure((size_t)chunk * h->M * sizeof(uint16_t)));
@@ -891,7 +932,10 @@ int vaqgpu_add_codes_synthetic(vaqgpu_t *h, int64_t n, uint64_t seed, const floa
   if (n == 0) return VAQGPU_OK;
   if (h->n_rows + n > 0x7FFFFFFFll) return fail(VAQGPU_EINVAL, "more than 2^31-1 rows per index");
   DeviceGuard g(h->device);
-  if (h->C) clear_clusters(h);
+  {
+    int rc_ = drop_clusters(h);
+    if (rc_) return rc_;
+  }
   CU(grow_codes(&h->d_codes, &h->cap_rows, h->n_rows, h->lay.W, h->n_rows + n, h->stream));
   const float *d_cdf = nullptr;
   if (cdf) {
@@ -937,8 +981,10 @@ int vaqgpu_get_codes_u16(vaqgpu_t *h, int64_t row0, int64_t n, uint16_t *out) {
   for (int64_t r = 0; r < n; r += chunk) {
     const int64_t c = std::min(chunk, n - r);
     // storage rows that can hold the original rows [row0 + r, row0 + r + c): the windows they fall into
-    const int64_t slo = h->d_rowid ? ((row0 + r) / kLayoutWin) * kLayoutWin : row0 + r;
-    const int64_t shi = h->d_rowid ? std::min<int64_t>(h->n_rows, ((row0 + r + c + kLayoutWin - 1) / kLayoutWin) * kLayoutWin) : row0 + r + c;
+    // (windows that follow TI clusters are not aligned: every stored row is a candidate then)
+    const int64_t slo = !h->d_rowid ? row0 + r : h->cluster_windows ? 0 : ((row0 + r) / kLayoutWin) * kLayoutWin;
+    const int64_t shi = !h->d_rowid ? row0 + r + c
+                        : h->cluster_windows ? h->n_rows : std::min<int64_t>(h->n_rows, ((row0 + r + c + kLayoutWin - 1) / kLayoutWin) * kLayoutWin);
     CU(launch_unpack_codes(h->d_codes, row0 + r, c, h->lay, (uint16_t *)h->w_stage.p, h->d_rowid, slo, shi, h->stream));
     CU(cudaMemcpyAsync(out + (size_t)r * h->M, h->w_stage.p, (size_t)c * h->M * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1059,6 +1105,8 @@ int vaqgpu_set_clusters(vaqgpu_t *h, const float *clusters, int32_t C, int32_t s
     return fail(e == cudaErrorMemoryAllocation ? VAQGPU_ENOMEM : VAQGPU_ECUDA, "vaqgpu_set_clusters: %s", cudaGetErrorString(e));
   }
   h->C = C; h->segdims = segdims;
+  h->h_cl_start.assign(start, start + C);
+  h->h_cl_size.assign(size, size + C);
   return VAQGPU_OK;
 }
 
@@ -1137,6 +1185,9 @@ int vaqgpu_cluster_ti(vaqgpu_t *h, int32_t C, int32_t n_segments, int32_t iters)
   h->d_tile_cl = tile_cl; tile_cl = nullptr;
   h->C = C; h->segdims = seg * h->L;
   h->opt_n = 0;
+  h->h_cl_start.resize(C); h->h_cl_size.resize(C);
+  cudaMemcpy(h->h_cl_start.data(), h->d_cl_start, (size_t)C * sizeof(int64_t), cudaMemcpyDeviceToHost);
+  cudaMemcpy(h->h_cl_size.data(), h->d_cl_size, (size_t)C * sizeof(int64_t), cudaMemcpyDeviceToHost);
   cleanup();
   return VAQGPU_OK;
 }
