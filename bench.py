@@ -730,6 +730,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sift1m_256b_m32_k10", choices=sorted(WORKLOADS))
     ap.add_argument("--queries", type=int, default=0, help="override the workload's query count")
+    ap.add_argument("--rows", type=int, default=0, help="override the workload's row count (rehearsals; the result is not the named config)")
+    ap.add_argument("--visit", type=float, default=0.0, help="override the TI workload's visit fraction")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="host row slice for the CPU baseline of device-generated workloads")
     ap.add_argument("--no-cpu", action="store_true")
@@ -749,6 +751,13 @@ def main():
     w = dict(WORKLOADS[args.workload])
     if args.queries:
         w["nq"] = args.queries
+    if args.rows:
+        w["n"] = args.rows
+        w["desc"] += f" [rows overridden: {args.rows}]"
+        if "ham_rows" in w:
+            w["ham_rows"] = args.rows
+    if args.visit and "visit" in w:
+        w["visit"] = args.visit
     if args.impl == "reference":
         run_reference_arm(args, w, args.workload)
     else:
