@@ -491,8 +491,9 @@ def quarter_conflicts(codes, order, nf=4):
     return float(onehot.max(2).mean())
 
 
-def test_conflict_aware_layout_is_invisible_and_effective(port):
+def test_conflict_aware_layout_is_invisible_and_effective(port, monkeypatch):
     from vaq_b200.index import EA, PROJECTED
+    monkeypatch.setenv("VAQGPU_TUNE", "order=0")          # aligned windows only (the scan order has its own test below)
     rng = np.random.default_rng(31)
     bits = [9, 9, 9, 9, 8, 8, 7, 7, 7, 7, 6, 6]
     m = random_model(rng, len(bits), 2, bits)
@@ -517,6 +518,55 @@ def test_conflict_aware_layout_is_invisible_and_effective(port):
     assert np.array_equal(np.sort(order), np.arange(n1 + n2)) and np.array_equal(order // 4096, np.arange(n1 + n2) // 4096)
     assert quarter_conflicts(codes, order) < 1.6
     assert np.array_equal(ix.get_codes(), codes)
+    ix.close()
+
+
+def test_scan_order_is_invisible(port, monkeypatch):
+    """Indexes of 32 K .. 8 M rows are grouped by coarse cluster before the first search (scan order, vaqgpu_host.cu
+    build_scan_order) and the query tiles start at their nearest cluster: ids, distances, codes read back, appended
+    rows (tail, then re-clustering) and a later vaqgpu_set_clusters must all behave as if the rows had never moved."""
+    from vaq_b200.index import EA, HEAP, PROJECTED, SQRT, TI
+    rng = np.random.default_rng(77)
+    bits = [9, 9, 9, 9, 8, 8, 7, 7, 7, 7, 6, 6]
+    m = random_model(rng, len(bits), 2, bits)
+    n1, n2, n3 = 40000, 3000, 20000
+    codes = random_codes(rng, m, n1 + n2 + n3)
+    codes[5000:5100] = codes[:100]                                               # ties across clusters' members
+    Q = rng.standard_normal((41, m.D)).astype(np.float32)
+    Q[:8] = np.concatenate([m.centroids[s][codes[:8, s]] for s in range(m.M)], 1)  # queries that sit on rows
+    ix = make_index(m, codes=codes[:n1])
+    check_search(port, m, codes[:n1], Q, 10, EA, ix=ix)
+    order = ix.get_row_order()
+    assert np.array_equal(np.sort(order), np.arange(n1))
+    assert not np.array_equal(order // 4096, np.arange(n1) // 4096)              # rows crossed windows: grouped by cluster
+    assert np.array_equal(ix.get_codes(), codes[:n1])
+    assert np.array_equal(ix.get_codes(12345, 777), codes[12345:12345 + 777])
+    check_search(port, m, codes[:n1], Q[:1], 10, HEAP, ix=ix)                    # one query, padded tile
+    check_search(port, m, codes[:n1], Q[:9], 100, EA, ix=ix)                     # two tiles, k = 100
+    monkeypatch.setenv("VAQGPU_TUNE", "chunks=3")                                # several row chunks: the start chunk rotates too
+    check_search(port, m, codes[:n1], Q, 10, EA, ix=ix)
+    monkeypatch.delenv("VAQGPU_TUNE")
+    ix.add_codes(codes[n1:n1 + n2])                                              # tail after the clusters
+    check_search(port, m, codes[:n1 + n2], Q, 10, EA, ix=ix)
+    order2 = ix.get_row_order()
+    assert np.array_equal(order2[:n1] < n1, np.ones(n1, bool)) and np.array_equal(np.sort(order2[n1:]), np.arange(n1, n1 + n2))
+    assert np.array_equal(ix.get_codes(), codes[:n1 + n2])
+    ix.add_codes(codes[n1 + n2:])                                                # outgrows the tail: clustered again
+    check_search(port, m, codes, Q, 10, EA, ix=ix)
+    order3 = ix.get_row_order()
+    assert np.array_equal(np.sort(order3), np.arange(codes.shape[0])) and (order3[:n1] >= n1).any()
+    assert np.array_equal(ix.get_codes(), codes)
+    # TI clusters afterwards: arrival order again, exact TI answers
+    C = 50
+    sizes = np.full(C, codes.shape[0] // C, np.int64); sizes[-1] += codes.shape[0] - sizes.sum()
+    start = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+    clusters = rng.standard_normal((C, 8)).astype(np.float32)
+    ix.set_clusters(clusters, start, sizes, np.arange(codes.shape[0], dtype=np.int32))
+    assert np.array_equal(ix.get_row_order(), np.arange(codes.shape[0]))
+    ix.set_visit(1.0)
+    lab, dis = ix.search(Q, 10, TI | EA | PROJECTED)
+    want_lab, want_dis = port.search_lex(m, codes, Q, 10)
+    assert np.array_equal(lab, want_lab) and bitwise_equal(dis, want_dis)
     ix.close()
 
 

@@ -7,10 +7,12 @@ without an sm_100 GPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libvaqgpu.so"
+# VAQGPU_LIB: development only (e.g. a -DVAQGPU_STATS build next to the release library)
+LIB_PATH = Path(os.environ["VAQGPU_LIB"]) if os.environ.get("VAQGPU_LIB") else PKG / "libvaqgpu.so"
 
 VAQGPU_OK, VAQGPU_EINVAL, VAQGPU_ECUDA, VAQGPU_ENOMEM, VAQGPU_ESTATE = 0, -1, -2, -3, -4
 # search flags (include/vaqgpu.h; low byte == VAQ::NNMethod, reference VAQ.hpp:38-49)

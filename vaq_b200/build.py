@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     nvcc = _nvcc()
     OBJ.mkdir(exist_ok=True)
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("VAQGPU_EXTRA_NVCC", "").split()      # development: e.g. -DVAQGPU_STATS
 
     def compile_one(src: Path):
         obj = OBJ / (src.stem + ".o")

@@ -104,7 +104,13 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   const int k = a.k;
   // grid: query tiles on x, row chunks on y (all tiles sweep a chunk while it is L2-resident); chunks_fast swaps them
   // so that the chunks of one query tile run concurrently and share their bounds (few queries, development)
-  const int qt = a.chunks_fast ? blockIdx.y : blockIdx.x, chunk = a.chunks_fast ? blockIdx.x : blockIdx.y;
+  const int qt = a.chunks_fast ? blockIdx.y : blockIdx.x;
+  int chunk = a.chunks_fast ? blockIdx.x : blockIdx.y;
+  if (a.rot_tile) {          // scan order: the chunk that holds the query tile's nearest rows goes first
+    const int nch = (int)(a.chunks_fast ? gridDim.x : gridDim.y);
+    chunk += (int)(((int64_t)__ldg(a.rot_tile + qt) - a.tile_lo) / a.chunk_tiles);
+    if (chunk >= nch) chunk -= nch;
+  }
   const int q0 = qt * T8;
 
   const size_t lut_bytes = (size_t)a.lut_stride * T8 * sizeof(__half);       // multiple of 64
@@ -130,14 +136,22 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
     for (int l = 0; l < 3; l++) atomic_min_half(thr_h + l * 4 + (t >> 1), t & 1, half_bits_ru(v * margin[l]));
   };
 
-  long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kDbgSlots : nullptr;
+#ifdef VAQGPU_STATS
+  // development build (-DVAQGPU_STATS): per-CTA event counts (slots 8..) and warp-0 clocks per level (slots 20..)
+  unsigned long long st_cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long st_clk[4] = {0, 0, 0, 0};
+#define STAT(i, v) st_cnt[i] += (v)
+#else
+#define STAT(i, v)
+#endif
   if (dbg && tid == 0) dbg[0] = clock64();
   for (int i = tid; i < T8 * k; i += blockDim.x) lists[i] = kEmptyKey;
   // index of a tile slot in the per-query bound arrays: the query's position in the caller's batch (TI searches run
   // the queries in tile order — a permutation that may differ between shards, while the bound arrays are exchanged)
   auto bound_index = [&](int t) -> int {
     const int q = min(q0 + t, a.nq - 1);
-    if constexpr (TI) return a.qmap[q]; else return q;
+    return a.qmap ? a.qmap[q] : q;
   };
   if (tid < T8) {
     const uint32_t g = a.thr_global[bound_index(tid)];
@@ -207,23 +221,43 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   const int64_t row_base = tile_begin << 5;
   const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
 
-  // this warp's tiles: warp, warp + nwarps, ... ; an iteration takes TPI consecutive ones of them, the next TPI are
-  // prefetched in registers
+  // Scan order.  The chunk's tiles are visited in rotated order, as two contiguous segments: [rot, n) first, then
+  // [0, rot), where rot is the tile at which the rows nearest to this query tile begin (rows grouped by coarse cluster
+  // at index time, queries grouped into tiles by nearest cluster: the first rows scanned already hold near neighbours,
+  // so the k-th-best bounds are tight after ~1 % of the chunk instead of converging like k/n).  rot = 0 without a
+  // scan order: one segment.
+  int rot = 0;
+  if (a.rot_tile) {
+    const int64_t r = (int64_t)__ldg(a.rot_tile + qt) - tile_begin;
+    rot = (r > 0 && r < tile_end - tile_begin) ? (int)r : 0;
+  }
+  int seg_base = rot;                                    // first tile of the current segment, relative to the chunk
+  int n_it = (int)(tile_end - tile_begin) - rot;         // its tiles
+  int seg_left = rot;                                    // tiles of the segment still to come
+  // this warp's tiles of a segment: warp, warp + nwarps, ... ; an iteration takes TPI consecutive ones of them, the
+  // next TPI are prefetched in registers
   uint4 cur[TPI], nxt[TPI];
   const size_t pstep = (size_t)nwarps * W * kTileRows;
-  const uint4 *pnext = a.codes + ((size_t)(tile_begin + warp) * W) * kTileRows + lane + TPI * pstep;     // first tile of `nxt`
-#pragma unroll
-  for (int u = 0; u < TPI; u++) {
-    cur[u] = nxt[u] = make_uint4(0, 0, 0, 0);
-    if (tile_begin + warp + u * nwarps < tile_end) cur[u] = ldg_stream_u4(pnext - (TPI - u) * pstep);
-    if (tile_begin + warp + (TPI + u) * nwarps < tile_end) nxt[u] = ldg_stream_u4(pnext + u * pstep);
-  }
+  const uint4 *pnext;                                    // first tile of `nxt`
   uint32_t ci_cur = 0u, ci_nxt = 0u;      // TI: cluster of this warp's current / next row tile
-  if constexpr (TI) {
-    if (tile_begin + warp < tile_end) ci_cur = (uint32_t)__ldg(a.tile_cl + tile_begin + warp);
-    if (tile_begin + warp + nwarps < tile_end) ci_nxt = (uint32_t)__ldg(a.tile_cl + tile_begin + warp + nwarps);
-  }
-  int refresh = 0;
+  int it;                                 // tile index relative to the segment (a chunk has at most 32768 tiles)
+  auto begin_segment = [&]() {
+    it = warp;
+    pnext = a.codes + ((size_t)(tile_begin + seg_base + warp) * W) * kTileRows + lane + TPI * pstep;
+#pragma unroll
+    for (int u = 0; u < TPI; u++) {
+      cur[u] = nxt[u] = make_uint4(0, 0, 0, 0);
+      if (warp + u * nwarps < n_it) cur[u] = ldg_stream_u4(pnext - (TPI - u) * pstep);
+      if (warp + (TPI + u) * nwarps < n_it) nxt[u] = ldg_stream_u4(pnext + u * pstep);
+    }
+    if constexpr (TI) {
+      if (warp < n_it) ci_cur = (uint32_t)__ldg(a.tile_cl + tile_begin + seg_base + warp);
+      if (warp + nwarps < n_it) ci_nxt = (uint32_t)__ldg(a.tile_cl + tile_begin + seg_base + warp + nwarps);
+    }
+  };
+  begin_segment();
+  // bound refresh counter: steps of 2, the low bit set in the lanes that never refresh (no query of the tile in them)
+  int refresh = (lane < T8 && q0 + lane < a.nq) ? 0 : 1;
   const uint32_t rows_here = (uint32_t)(min(a.n_rows, tile_end << 5) - row_base);    // valid rows of this chunk
 
   // ---- bound seeding ---------------------------------------------------------------------------------
@@ -241,7 +275,7 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   // A search of one or two query tiles over many chunks (the HBM-bound regime) runs all its CTAs at once on the same
   // queries: their exact bounds pool through thr_global within microseconds, so a quarter of the sample is enough.
   const unsigned grid_chunks = a.chunks_fast ? gridDim.x : gridDim.y, grid_qtiles = a.chunks_fast ? gridDim.y : gridDim.x;
-  const int spl = (int)min((grid_chunks >= 32u && grid_qtiles <= 2u) ? 1u : 4u, rows_here / (blockDim.x * 4u));
+  const int spl = (int)min((grid_chunks >= 32u && grid_qtiles <= 2u) ? 1u : (unsigned)a.seed_rows, rows_here / (blockDim.x * 4u));
   int unbounded = 0;
   if (tid < T8 && q0 + tid < a.nq) unbounded = thr_f[tid] == 0xFFFFFFFFu;
   if (a.seed && k <= (int)blockDim.x && spl >= 1 && M <= 64 && __syncthreads_or(unbounded)) {
@@ -249,7 +283,13 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
     __half2 best[4];
     best[0] = best[1] = best[2] = best[3] = as_h2(0x7C007C00u);        // +inf
     for (int j = 0; j < spl; j++) {
-      const int64_t row = row_base + (int64_t)((uint32_t)(j * (int)blockDim.x + tid) * step);
+      // sample: evenly spaced rows of the chunk; with a scan order the rows the scan starts with (the nearest ones)
+      uint32_t rr = (uint32_t)(j * (int)blockDim.x + tid) * step;
+      if (a.rot_tile) {
+        rr = ((uint32_t)rot << 5) + (uint32_t)(j * (int)blockDim.x + tid);
+        if (rr >= rows_here) rr -= rows_here;
+      }
+      const int64_t row = row_base + (int64_t)rr;
       const uint32_t *rp = codes32 + (((size_t)(row >> 5) * W) * kTileRows + (row & 31)) * 4;
       uint32_t wd[8];
       if constexpr (W <= 2) {           // row words once into registers (same sliding window as the queue passes)
@@ -343,18 +383,19 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
     __syncthreads();
   }
   if (dbg && tid == 0) dbg[2] = clock64();
-  // 32-bit loop state: tile index relative to the chunk (a chunk has at most 32768 tiles)
-  int it = warp;
-  const int n_it = (int)(tile_end - tile_begin);
   const uint32_t q1_s = smem_u32(q1);
   int dbg_tail = 0;
 
   while (true) {
+    if (it >= n_it && seg_left > 0) {          // on to the rows before the start tile
+      seg_base = 0; n_it = seg_left; seg_left = 0;
+      begin_segment();
+    }
     if (dbg && it >= n_it && !dbg_tail && tid == 0) { dbg[3] = clock64(); dbg_tail = 1; }
     // ---- what next: a queue that holds a full pass goes first (deepest level first: it feeds nothing further and
     // frees the bounds), otherwise stage 1 streams tiles until the level-1 queue fills, at the end everything drains
     int level = 0, take = 0;
-    if (q3n >= q3_need) { level = 3; take = min(q3n, 32); if (q3_eager > 0) q3_eager--; else q3_need = min(32, 2 * q3_need); }
+    if (q3n >= q3_need) { level = 3; take = min(q3n, 32); if (q3_eager > 0) q3_eager--; else q3_need = min(a.q3_cap, 2 * q3_need); }
     else if (q2n >= q2_need) { level = 2; take = min(q2n, 32); q2_need = min(32, 2 * q2_need); }
     else if (q1n >= 32) { level = 1; take = 32; }
     else if (it < n_it) {
@@ -369,7 +410,7 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
           if (it + (2 * TPI + u) * nwarps < n_it) nxt[u] = ldg_stream_u4(pnext + u * pstep);
         if (a.l2_prefetch > 0 && (lane & 7) == 0 && it + (2 * TPI + a.l2_prefetch) * nwarps < n_it)
           prefetch_l2(pnext + (size_t)a.l2_prefetch * pstep);      // first words of a later tile, one 128-byte line per 8 lanes
-        if (((++refresh) & (TPI == 2 ? 15 : 31)) == 0 && lane < T8 && q0 + lane < a.nq) {
+        if (((refresh += 2) & (TPI == 2 ? 31 : 63)) == 0) {
           // pick up bounds published by other row chunks of this query tile (and, row-sharded, by other GPUs)
           const uint32_t g = *reinterpret_cast<volatile uint32_t *>(a.thr_global + bound_index(lane));
           if (g < *reinterpret_cast<volatile uint32_t *>(thr_f + lane)) publish_bound(lane, g);
@@ -383,9 +424,9 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
             const int itu = it + u * nwarps;
             const uint32_t ci = ci_cur;          // loaded one iteration ago (TPI == 1 in TI mode)
             ci_cur = ci_nxt;
-            ci_nxt = itu + 2 * nwarps < n_it ? (uint32_t)__ldg(a.tile_cl + tile_begin + itu + 2 * nwarps) : 0u;
+            ci_nxt = itu + 2 * nwarps < n_it ? (uint32_t)__ldg(a.tile_cl + tile_begin + seg_base + itu + 2 * nwarps) : 0u;
             if (ci != 0xFFFFu) cm = smask[ci];
-            else cm = smask[cluster_of_row(a.cl_start, a.C, row_base + ((int64_t)itu << 5) + lane)];
+            else cm = smask[cluster_of_row(a.cl_start, a.C, row_base + ((int64_t)(seg_base + itu) << 5) + lane)];
             if (!__any_sync(0xffffffffu, cm != 0u)) { sb[u] = 0u; continue; }          // nobody visits: no gathers
           }
           const uint4 w0 = w[u];
@@ -419,12 +460,13 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
 #pragma unroll
         for (int u = 0; u < TPI; u++) {
           const int itu = it + u * nwarps;
-          const uint32_t rel = ((uint32_t)itu << 5) + lane;
-          if (itu >= n_it || (itu == n_it - 1 && rel >= rows_here)) sb[u] = 0u;      // past the chunk / the partial last tile of the index
+          const uint32_t rel = ((uint32_t)(seg_base + itu) << 5) + lane;
+          if (itu >= n_it || rel >= rows_here) sb[u] = 0u;      // past the segment / the partial last tile of the index
           // compact the rows that still have a live query into the warp's queue
           const unsigned m = __ballot_sync(0xffffffffu, sb[u] != 0);
           if (sb[u]) sts32(q1_s + (uint32_t)(q1n + __popc(m & lt_mask)) * 4u, (rel << 8) | sb[u]);
           q1n += __popc(m);
+          STAT(0, lane == 0 ? __popc(m) : 0); STAT(9, __popc(sb[u]));
         }
         it += TPI * nwarps;
       } while (it < n_it && q1n < 32);
@@ -437,6 +479,10 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
     {
       // ---- 32 queued rows, one per lane (single code site for the three levels) -----------------------
       __syncwarp();
+#ifdef VAQGPU_STATS
+      const long long st_t0 = clock64();
+      if (lane == 0) st_cnt[level == 1 ? 1 : level == 2 ? 3 : 5] += 1;
+#endif
       const bool active = lane < take;
       uint32_t e = 0u;
       if (level == 1) { if (active) e = q1[q1n - take + lane]; q1n -= take; }
@@ -526,7 +572,9 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
           if (to_q2) q2[q2n + __popc(m & lt_mask)] = ne; else q3[q3n + __popc(m & lt_mask)] = ne;
         }
         if (to_q2) q2n += __popc(m); else q3n += __popc(m);
+        STAT(level == 1 ? 2 : 4, lane == 0 ? __popc(m) : 0);
       } else {
+#ifdef VAQGPU_OLD_EXACT
         // exact distances, one (row, query) pair per lane and pass, until every lane's mask is empty
         while (__any_sync(0xffffffffu, mask != 0)) {
           const bool act = mask != 0;
@@ -587,9 +635,87 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
             }
           }
         }
+#else
+        // exact distances, one (row, query) pair at a time with the lanes over the subspaces: every lane fetches the
+        // code of its subspace and the table entry, all M gathers are in flight together (one L2 / DRAM round trip per
+        // pair: a lane-per-pair loop has M/4 dependent ones), then the sum is formed in the reference's order and
+        // grouping — dism = ((l0+l1)+l2)+l3 inside each quad of lanes, dist += dism serially over the quads.
+        unsigned pend = __ballot_sync(0xffffffffu, mask != 0);
+        while (pend) {
+          const int src = __ffs(pend) - 1;
+          const unsigned msrc = __shfl_sync(0xffffffffu, mask, src);
+          const int t = __ffs(msrc) - 1;
+          if (lane == src) mask &= mask - 1;
+          if ((msrc & (msrc - 1u)) == 0u) pend &= pend - 1u;          // that was the last live query of this row
+          const int64_t prow = row_base + (__shfl_sync(0xffffffffu, e, src) >> 8);
+          const uint32_t *prp = codes32 + (((size_t)(prow >> 5) * W) * kTileRows + (prow & 31)) * 4;
+          STAT(6, lane == 0 ? 1 : 0); STAT(7, lane == 0 ? 1 : 0);
+          float dist = 0.f;
+          for (int f0 = 0; f0 < M; f0 += 32) {
+            const int f = f0 + lane;
+            float v = 0.f;
+            if (f < M) {
+              const uint32_t meta = a.lay.fmeta[f];
+              const uint32_t code = __funnelshift_r(__ldg(prp + a.lay.fw_lo[f]), __ldg(prp + a.lay.fw_hi[f]), meta & 31u) & (meta >> 16);
+              v = __ldg(g32 + (size_t)(a.lay.foff[f] + code) * T8 + t);
+            }
+            // quads: lane 4g ends up with ((l0 + l1) + l2) + l3 (a partial last quad adds exact zeros)
+            float dism = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1));
+            dism = __fadd_rn(dism, __shfl_down_sync(0xffffffffu, v, 2));
+            dism = __fadd_rn(dism, __shfl_down_sync(0xffffffffu, v, 3));
+            const int ng = min(8, (M - f0 + 3) >> 2);
+            for (int g = 0; g < ng; g++) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dism, 4 * g));
+          }
+          // one observer per decision: other warps lower the bounds and lists concurrently, and every branch below
+          // must be warp-uniform (the lanes meet again in full-mask shuffles)
+          const float thr = __uint_as_float(__shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(thr_f + t), 0));
+          if (dist > thr) continue;
+          // keys carry the ORIGINAL row index (the storage order is conflict-aware, layout.cu): canonical (distance, id) order
+          const uint64_t kk = make_key_f32(dist, a.rowid ? (int32_t)__ldg(a.rowid + prow) : (int32_t)prow);
+          volatile uint64_t *lst = lists + (size_t)t * k;
+          {
+            uint64_t c = lst[k - 1];
+            c = __shfl_sync(0xffffffffu, c, 0);      // one observer: the decision must be warp-uniform
+            if (!(kk < c)) continue;
+          }
+          STAT(8, lane == 0 ? 1 : 0);
+          // take the query's list lock; give up as soon as the list has moved past this candidate
+          int got = 0;
+          if (lane == 0) {
+            while (true) {
+              if (!(kk < lst[k - 1])) break;
+              if (atomicCAS(locks + t, 0u, 1u) == 0u) { got = 1; break; }
+              __nanosleep(100);
+            }
+          }
+          got = __shfl_sync(0xffffffffu, got, 0);
+          if (!got) continue;
+          const uint64_t before = lst[k - 1];
+          const uint64_t kth = warp_list_insert(lst, k, kk, lane);
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence_block();
+            atomicExch(locks + t, 0u);
+            if (kth != before && kth != kEmptyKey) {
+              const uint32_t bits = (uint32_t)(kth >> 32);
+              publish_bound(t, bits);
+              publish_global_bound(a.thr_global, a.peers, bound_index(t), bits);
+            }
+          }
+        }
+#endif
       }
+#ifdef VAQGPU_STATS
+      st_clk[level] += clock64() - st_t0;
+#endif
     }
   }
+#ifdef VAQGPU_STATS
+  if (dbg) {
+    for (int i = 0; i < 10; i++) if (st_cnt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(dbg) + 8 + i, st_cnt[i]);
+    if (tid == 0) for (int i = 1; i < 4; i++) dbg[20 + i] = st_clk[i];
+  }
+#endif
 
   // ---- CTA epilogue: publish this (query tile, chunk)'s keys -----------------------------------------
   if (dbg && tid == 0) dbg[4] = clock64();

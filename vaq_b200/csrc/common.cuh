@@ -9,6 +9,7 @@ constexpr int kMaxSubspaces = 128;   // M
 constexpr int kMaxRowWords = 32;     // 32-bit words per packed row (<= 1024 bits)
 constexpr int kTileRows = 32;        // rows per tile == warp width
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kDbgSlots = 24;        // development: per-CTA slots of the filter kernel's phase clocks / event counts
 constexpr int kLayoutWin = 4096;     // rows per window of the conflict-aware row order (layout.cu); a multiple of kTileRows
 
 // fmeta bit layout: [4:0] shift inside the starting 32-bit word, [5] table spilled to
@@ -268,6 +269,8 @@ struct AdcFilter16Args {
   uint32_t *thr_global;
   PeerBounds peers;          // the same array on the other row shards (n = 0: single shard)
   int32_t seed;              // 1 = CTAs seed their bounds from sample rows of their chunk
+  int32_t q3_cap;            // rows the exact level waits for at most (1..32)
+  int32_t seed_rows;         // sample rows per lane of the bound seeding (at most a quarter of the chunk in total)
   const uint32_t *rowid;     // original row index of each storage row (layout.cu), or NULL = identity
   int32_t chunks_fast;       // grid order: 0 = query tiles fastest (default), 1 = row chunks fastest
   int32_t l2_prefetch;       // > 0: stage 1 prefetches into L2 this many iterations ahead (code matrix >> L2)
@@ -276,7 +279,9 @@ struct AdcFilter16Args {
   const uint16_t *tile_cl;
   const int64_t *cl_start;
   const uint8_t *tmask;
-  const int32_t *qmap;       // TI: position in the caller's batch of each tile slot (bound arrays are indexed by it)
+  const int32_t *qmap;       // queries re-grouped into tiles (TI, scan order): position in the caller's batch of each tile slot
+                             // (bound arrays are indexed by it); NULL = identity
+  const int32_t *rot_tile;   // [query tiles] row tile at which this query tile's scan starts (scan order, layout.cu), or NULL
   int32_t C;
   long long *dbg;            // development: per-CTA phase clocks (NULL = off)
   ScanLayout lay;
@@ -340,6 +345,7 @@ cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clus
                            cudaStream_t st);
 cudaError_t launch_tile_clusters(const int64_t *start, int C, int64_t n_rows, uint16_t *tile_cl, cudaStream_t st);
 // device-side clusterTI (cluster_ti.cu)
+cudaError_t launch_rot_tiles(const int32_t *nearest, const int32_t *perm, int nq, const int64_t *cl_start, int32_t *rot_tile, cudaStream_t st);
 size_t cluster_ti_table_floats(const LutPlan &plan, int seg, int C);
 size_t regroup_hist_ints(int64_t n, int C);
 cudaError_t launch_cluster_ti_kmeans(const uint4 *codes, const ScanLayout &lay, int64_t n, const LutPlan &plan, int seg,

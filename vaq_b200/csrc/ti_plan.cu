@@ -185,6 +185,20 @@ cudaError_t launch_ti_plan(const float *q_proj, int nq, int D, const float *clus
   return cudaGetLastError();
 }
 
+// rot_tile[t] = row tile in which the cluster nearest to the first query of query tile t begins
+__global__ void rot_tiles_kernel(const int32_t *__restrict__ nearest, const int32_t *__restrict__ perm, int n_qtiles,
+                                 const int64_t *__restrict__ cl_start, int32_t *__restrict__ rot_tile) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_qtiles) rot_tile[t] = (int32_t)(cl_start[nearest[perm[8 * t]]] >> 5);
+}
+
+cudaError_t launch_rot_tiles(const int32_t *nearest, const int32_t *perm, int nq, const int64_t *cl_start, int32_t *rot_tile, cudaStream_t st) {
+  const int n_qtiles = (nq + 7) / 8;
+  if (n_qtiles <= 0) return cudaSuccess;
+  rot_tiles_kernel<<<(n_qtiles + 255) / 256, 256, 0, st>>>(nearest, perm, n_qtiles, cl_start, rot_tile);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tile_clusters(const int64_t *start, int C, int64_t n_rows, uint16_t *tile_cl, cudaStream_t st) {
   const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
   if (n_tiles <= 0) return cudaSuccess;

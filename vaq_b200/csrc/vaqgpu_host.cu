@@ -57,6 +57,9 @@ constexpr int kScanThreads = 256;
 constexpr size_t kSmemCap = 227 * 1024;           // opt-in dynamic shared memory per CTA on sm_100
 constexpr size_t kLutWorkspaceBytes = 1ull << 30; // LUT workspace cap -> queries per launch
 constexpr int64_t kStageRows = 1 << 21;           // rows per upload / generate chunk
+// scan order (ensure_layout): indexes of this many rows are grouped by coarse cluster.  Below, a search is a handful of
+// microseconds per CTA anyway; above, the bounds of a query tile settle within the first percent of its rows without help.
+constexpr int64_t kOrderMinRows = 1 << 15, kOrderMaxRows = 1 << 23;
 
 struct DevBuf {
   void *p = nullptr;
@@ -136,7 +139,13 @@ struct vaqgpu_index {
   uint32_t *d_rowid = nullptr;
   int64_t rowid_cap = 0, rowid_n = 0, opt_n = 0;
   float layout_ms = 0.f;
-  bool cluster_windows = false;                  // the re-ordering windows follow the TI clusters (not aligned 4096-row blocks)
+  bool cluster_windows = false;                  // the re-ordering windows follow the TI / scan-order clusters (not aligned 4096-row blocks)
+  // scan order (EA / HEAP searches of an index without TI clusters): rows [0, oc_n) grouped by a coarse clustering of
+  // their leading subspaces so that a query tile can start its scan at the rows nearest to it (ensure_layout)
+  int32_t oc_C = 0, oc_dims = 0;
+  int64_t oc_n = 0;
+  float *d_oc_centres_t = nullptr;               // [oc_dims][oc_C]
+  int64_t *d_oc_start = nullptr, *d_oc_size = nullptr;
   std::vector<int64_t> h_cl_start, h_cl_size;    // host copies of the TI cluster ranges
 
   // cross-shard bound exchange (vaqgpu_bounds_*): two halves of bounds_cap entries, used alternately by
@@ -146,7 +155,7 @@ struct vaqgpu_index {
   PeerBounds peers{};
   std::vector<void *> ipc_opened;
 
-  DevBuf w_vis, w_near, w_perm, w_qperm, w_tmask, w_lsrc, w_lscratch, w_dbg, w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
+  DevBuf w_vis, w_near, w_perm, w_qperm, w_tmask, w_rot, w_lsrc, w_lscratch, w_dbg, w_lut16, w_scale, w_thr, w_q, w_qproj, w_lut, w_keys, w_scratch, w_ranges, w_nranges, w_stage, w_labels, w_dists, w_outkeys, w_cdf, w_x;
 };
 
 struct hamgpu_index {
@@ -358,11 +367,87 @@ int ensure_rowid(vaqgpu_index *h, cudaStream_t st) {
   return VAQGPU_OK;
 }
 
+void clear_scan_order(vaqgpu_index *h) {
+  cudaFree(h->d_oc_centres_t); cudaFree(h->d_oc_start); cudaFree(h->d_oc_size);
+  h->d_oc_centres_t = nullptr; h->d_oc_start = h->d_oc_size = nullptr;
+  h->oc_C = 0; h->oc_dims = 0; h->oc_n = 0;
+}
+
+int restore_layout(vaqgpu_index *h, cudaStream_t st);
+
+// Scan order: groups all rows (arrival order on entry) by a coarse k-means clustering of their decoded leading
+// subspaces (cluster_ti.cu, the machinery of the device-side clusterTI) and records the regrouping in rowid.
+// The reference has no counterpart; the answer of a search does not depend on it (keys carry rowid).
+int build_scan_order(vaqgpu_index *h, cudaStream_t st, std::vector<int64_t> &cl_start, std::vector<int64_t> &cl_size) {
+  const int64_t n = h->n_rows;
+  int C = 16;
+  while (C < 256 && (int64_t)C * 2048 < n) C *= 2;
+  C = tune_knob("order_c", C);
+  const int seg = std::min(h->M, std::max(1, 16 / std::max(1, h->L)));          // ~16 leading dimensions
+  const int iters = 6;
+  const size_t tbl = cluster_ti_table_floats(h->plan, seg, C);
+  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+  DevBuf centres, T, hist, assign, sizes, bh, id_map, ncodes;
+  float *centres_t = nullptr;
+  int64_t *start = nullptr, *size64 = nullptr;
+  auto cleanup = [&]() {
+    for (DevBuf *b : {&centres, &T, &hist, &assign, &sizes, &bh, &id_map, &ncodes}) b->release();
+    cudaFree(centres_t); cudaFree(start); cudaFree(size64);
+  };
+#define CO(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      cleanup();                                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? VAQGPU_ENOMEM : VAQGPU_ECUDA, "scan order: %s: %s", #call, cudaGetErrorString(e_)); \
+    }                                                                                                    \
+  } while (0)
+  CO(centres.ensure((size_t)C * seg * h->L * sizeof(float)));
+  CO(T.ensure(tbl * sizeof(float)));
+  CO(hist.ensure(tbl * sizeof(int32_t)));
+  CO(assign.ensure((size_t)n * sizeof(int32_t)));
+  CO(sizes.ensure((size_t)C * sizeof(int32_t)));
+  CO(bh.ensure(regroup_hist_ints(n, C) * sizeof(int32_t)));
+  CO(id_map.ensure((size_t)n * sizeof(int32_t)));
+  CO(ncodes.ensure((size_t)tiles * kTileRows * h->lay.W * sizeof(uint4)));
+  CO(cudaMalloc(&centres_t, (size_t)C * seg * h->L * sizeof(float)));
+  CO(cudaMalloc(&start, (size_t)C * sizeof(int64_t)));
+  CO(cudaMalloc(&size64, (size_t)C * sizeof(int64_t)));
+  CO(cudaMemsetAsync(ncodes.p, 0, (size_t)tiles * kTileRows * h->lay.W * sizeof(uint4), st));
+  CO(launch_cluster_ti_kmeans(h->d_codes, h->lay, n, h->plan, seg, h->d_centroids, h->d_cent_off, h->d_ent_off, C, iters, (float *)centres.p,
+                              (float *)T.p, (int32_t *)hist.p, (int32_t *)assign.p, (int32_t *)sizes.p, st));
+  CO(launch_regroup((const int32_t *)assign.p, (const int32_t *)sizes.p, n, C, h->d_codes, (uint4 *)ncodes.p, h->lay.W, (int32_t *)id_map.p, start,
+                    size64, (int32_t *)bh.p, st));
+  CO(launch_transpose((const float *)centres.p, C, seg * h->L, centres_t, st));
+  // the regrouped matrix replaces the rows in place (the allocation keeps its capacity); rowid = arrival index of each row
+  CO(cudaMemcpyAsync(h->d_codes, ncodes.p, (size_t)tiles * kTileRows * h->lay.W * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
+  CO(cudaMemcpyAsync(h->d_rowid, id_map.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  cl_start.resize(C); cl_size.resize(C);
+  CO(cudaMemcpyAsync(cl_start.data(), start, (size_t)C * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CO(cudaMemcpyAsync(cl_size.data(), size64, (size_t)C * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CO(cudaStreamSynchronize(st));
+#undef CO
+  clear_scan_order(h);
+  h->d_oc_centres_t = centres_t; centres_t = nullptr;
+  h->d_oc_start = start; start = nullptr;
+  h->d_oc_size = size64; size64 = nullptr;
+  h->oc_C = C; h->oc_dims = seg * h->L; h->oc_n = n;
+  cleanup();
+  return VAQGPU_OK;
+}
+
 // Re-orders the windows that hold rows added since the last call (the filter kernels call this before scanning).
 // With TI clusters set the windows are pieces of the clusters (<= kLayoutWin rows each), so every cluster keeps its
-// row range and the cluster-of-tile map stays valid.
+// row range and the cluster-of-tile map stays valid.  Without TI clusters, an index of kOrderMinRows..kOrderMaxRows rows
+// is first grouped by coarse cluster (scan order, above): the windows are then pieces of those clusters, and rows
+// appended later form a tail after them (re-clustered once the tail outgrows an eighth of the index).
 int ensure_layout(vaqgpu_index *h, cudaStream_t st) {
   if (h->n_rows <= h->opt_n || tune_knob("layout", 1) == 0) return ensure_rowid(h, st);
+  const bool order_ok = h->C == 0 && tune_knob("order", 1) != 0 && h->n_rows >= tune_knob("order_min", (int)kOrderMinRows) && h->n_rows <= kOrderMaxRows;
+  if (h->oc_C > 0 && !order_ok) {          // outgrew the scan order: back to arrival order, aligned windows
+    int rc = restore_layout(h, st);
+    if (rc) return rc;
+  }
   if (!h->d_rowid) {
     const int64_t cap = std::max(h->cap_rows, h->n_rows);
     CU(cudaMalloc(&h->d_rowid, (size_t)cap * sizeof(uint32_t)));
@@ -374,14 +459,36 @@ int ensure_layout(vaqgpu_index *h, cudaStream_t st) {
   int64_t n_windows = (h->n_rows - row_lo + kLayoutWin - 1) / kLayoutWin;
   const int64_t *d_win = nullptr;
   DevBuf w_win;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, st));
+  std::vector<int64_t> tab;
+  auto pieces = [&](int64_t start, int64_t size) {
+    for (int64_t off = 0; off < size; off += kLayoutWin) {
+      tab.push_back(start + off);
+      tab.push_back(std::min<int64_t>(kLayoutWin, size - off));
+    }
+  };
+  bool explicit_windows = false;
   if (h->C > 0) {
-    std::vector<int64_t> tab;
-    for (int c = 0; c < h->C; c++)
-      for (int64_t off = 0; off < h->h_cl_size[c]; off += kLayoutWin) {
-        tab.push_back(h->h_cl_start[c] + off);
-        tab.push_back(std::min<int64_t>(kLayoutWin, h->h_cl_size[c] - off));
-      }
+    for (int c = 0; c < h->C; c++) pieces(h->h_cl_start[c], h->h_cl_size[c]);
     row_lo = 0;
+    explicit_windows = true;
+  } else if (order_ok) {
+    if (h->oc_C == 0 || h->n_rows - h->oc_n > h->oc_n / 8) {
+      if (h->opt_n > 0) { rc = restore_layout(h, st); if (rc) return rc; rc = ensure_rowid(h, st); if (rc) return rc; }
+      std::vector<int64_t> cs, cz;
+      rc = build_scan_order(h, st, cs, cz);
+      if (rc) return rc;
+      for (size_t c = 0; c < cs.size(); c++) pieces(cs[c], cz[c]);
+      row_lo = 0;
+    } else {
+      pieces(h->oc_n, h->n_rows - h->oc_n);          // the tail: rows appended after the clustering
+      row_lo = h->oc_n;
+    }
+    explicit_windows = true;
+  }
+  if (explicit_windows) {
     n_windows = (int64_t)tab.size() / 2;
     if (n_windows > 0) {
       CU(w_win.ensure(tab.size() * sizeof(int64_t)));
@@ -394,9 +501,6 @@ int ensure_layout(vaqgpu_index *h, cudaStream_t st) {
   const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(n_windows, 2 * h->num_sms));
   CU(h->w_lsrc.ensure((size_t)(h->n_rows - row_lo) * sizeof(uint16_t)));
   CU(h->w_lscratch.ensure(layout_scratch_bytes(h->lay.W, ctas)));
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-  CU(cudaEventRecord(e0, st));
   CU(launch_layout(h->d_codes, row_lo, h->n_rows, h->lay, h->d_rowid, (uint16_t *)h->w_lsrc.p, (uint4 *)h->w_lscratch.p, ctas, d_win,
                    n_windows, st));
   CU(cudaEventRecord(e1, st));
@@ -428,6 +532,7 @@ int restore_layout(vaqgpu_index *h, cudaStream_t st) {
   if (e != cudaSuccess) return fail(VAQGPU_ECUDA, "restore_layout: %s", cudaGetErrorString(e));
   h->opt_n = 0;
   h->cluster_windows = false;
+  clear_scan_order(h);
   return VAQGPU_OK;
 }
 
@@ -507,9 +612,11 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       CU(launch_fill_u32(next, h->bounds_cap, 0xFFFFFFFFu, st));
       h->bounds_parity ^= 1;
     } else {
+      const bool fresh = h->w_thr.p == nullptr;
       CU(h->w_thr.ensure((size_t)nq * sizeof(uint32_t)));
       thr_all = (uint32_t *)h->w_thr.p;
-      CU(launch_fill_u32(thr_all, nq, 0xFFFFFFFFu, st));
+      // development (VAQGPU_TUNE=keepthr=1): repeat searches of the same batch start from the previous search's final bounds
+      if (fresh || !tune_knob("keepthr", 0)) CU(launch_fill_u32(thr_all, nq, 0xFFFFFFFFu, st));
     }
     launches++;
   }
@@ -536,12 +643,16 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     CU(h->w_scale.ensure((size_t)qb_max * sizeof(float)));
     CU(h->w_keys.ensure((size_t)qb_max * out_slots * k * sizeof(uint64_t)));
     if (out_slots > 16) CU(h->w_scratch.ensure((size_t)2 * qb_max * ((out_slots + 15) / 16) * k * sizeof(uint64_t)));
-    if (ti) {
-      CU(h->w_vis.ensure((size_t)qb_max * h->C));
+    // queries are re-grouped into tiles by nearest cluster: TI clusters (TI search) or the scan-order clusters
+    const bool ordered = !ti && h->oc_C > 0 && h->C == 0 && tune_knob("rot", 1) != 0;
+    const int plan_C = ti ? h->C : ordered ? h->oc_C : 0;
+    if (plan_C > 0) {
+      CU(h->w_vis.ensure((size_t)qb_max * plan_C));
       CU(h->w_near.ensure((size_t)qb_max * sizeof(int32_t)));
       CU(h->w_perm.ensure((size_t)qb_max * sizeof(int32_t)));
       CU(h->w_qperm.ensure((size_t)qb_max * h->D * sizeof(float)));
-      CU(h->w_tmask.ensure((size_t)(qb_max / T) * h->C));
+      CU(h->w_tmask.ensure((size_t)(qb_max / T) * plan_C));
+      CU(h->w_rot.ensure((size_t)(qb_max / T) * sizeof(int32_t)));
     }
 
     for (int q0 = 0; q0 < nq; q0 += qb_max) {
@@ -555,6 +666,17 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
                           (uint8_t *)h->w_tmask.p, st));
         qp = (const float *)h->w_qperm.p;          // the batch in tile order
         launches += 3;
+        if (tune_knob("rot", 1) != 0) {
+          CU(launch_rot_tiles((const int32_t *)h->w_near.p, (const int32_t *)h->w_perm.p, qb, h->d_cl_start, (int32_t *)h->w_rot.p, st));
+          launches++;
+        }
+      } else if (ordered) {
+        // nearest scan-order cluster of each query, queries grouped into tiles by it, start tile of each query tile
+        CU(launch_ti_plan(qp, qb, h->D, h->d_oc_centres_t, h->oc_C, h->oc_dims, h->d_oc_size, 1.f, k, (uint8_t *)h->w_vis.p,
+                          (int32_t *)h->w_near.p, (int32_t *)h->w_perm.p, (float *)h->w_qperm.p, (uint8_t *)h->w_tmask.p, st));
+        CU(launch_rot_tiles((const int32_t *)h->w_near.p, (const int32_t *)h->w_perm.p, qb, h->d_oc_start, (int32_t *)h->w_rot.p, st));
+        qp = (const float *)h->w_qperm.p;
+        launches += 4;
       }
       CU(launch_lut_build(qp, qb, qb_pad, h->D, h->d_centroids, h->d_cent_rmax, plan, (float *)h->w_lut.p, h->w_lut16.p,
                           (float *)h->w_scale.p, st));
@@ -571,10 +693,16 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.peers = peers;
       for (int i = 0; i < peers.n; i++) a.peers.p[i] += q0;
       a.seed = tune_knob("seed", 1);
+      a.q3_cap = std::max(1, std::min(32, tune_knob("q3cap", 32)));
+      a.seed_rows = std::max(1, std::min(16, tune_knob("spl", 4)));
       a.rowid = h->d_rowid;
       if (ti) {
         a.tile_cl = h->d_tile_cl; a.cl_start = h->d_cl_start; a.tmask = (const uint8_t *)h->w_tmask.p; a.C = h->C;
         a.qmap = (const int32_t *)h->w_perm.p;
+        if (tune_knob("rot", 1) != 0) a.rot_tile = (const int32_t *)h->w_rot.p;
+      } else if (ordered) {
+        a.qmap = (const int32_t *)h->w_perm.p;
+        a.rot_tile = (const int32_t *)h->w_rot.p;
       }
       a.chunks_fast = tune_knob("chunks_fast", 0);
       // a code matrix far larger than L2 streams from HBM: keep more of it in flight than the register prefetch holds
@@ -582,17 +710,29 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       a.lay = lay;
       const bool dbg = tune_knob("dbg", 0) != 0;
       const size_t n_cta = (size_t)((qb + T - 1) / T) * n_chunks;
-      if (dbg) { CU(h->w_dbg.ensure(n_cta * 8 * sizeof(long long))); a.dbg = (long long *)h->w_dbg.p; }
+      if (dbg) {
+        CU(h->w_dbg.ensure(n_cta * kDbgSlots * sizeof(long long)));
+        CU(cudaMemsetAsync(h->w_dbg.p, 0, n_cta * kDbgSlots * sizeof(long long), st));
+        a.dbg = (long long *)h->w_dbg.p;
+      }
       CU(launch_adc_filter16_scan(a, threads, smem, st));
       if (dbg) {        // development only: per-CTA phase durations in SM clocks
-        std::vector<long long> hd(n_cta * 8);
+        std::vector<long long> hd(n_cta * kDbgSlots);
         CU(cudaStreamSynchronize(st));
         CU(cudaMemcpy(hd.data(), h->w_dbg.p, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         double ph[5] = {0, 0, 0, 0, 0};
         for (size_t c = 0; c < n_cta; c++)
-          for (int i = 0; i < 5; i++) ph[i] += (double)(hd[c * 8 + i + 1] - hd[c * 8 + i]);
+          for (int i = 0; i < 5; i++) ph[i] += (double)(hd[c * kDbgSlots + i + 1] - hd[c * kDbgSlots + i]);
         fprintf(stderr, "[vaqgpu dbg] per-CTA clocks: table staging %.0f, seeding %.0f, scan (warp 0) %.0f, warp-0 tail %.0f, wait for other warps %.0f\n",
                 ph[0] / n_cta, ph[1] / n_cta, ph[2] / n_cta, ph[3] / n_cta, ph[4] / n_cta);
+        double sc[16] = {0};
+        for (size_t c = 0; c < n_cta; c++)
+          for (int i = 0; i < 16; i++) sc[i] += (double)hd[c * kDbgSlots + 8 + i];
+        if (sc[0] > 0)        // -DVAQGPU_STATS build
+          fprintf(stderr, "[vaqgpu stats] per CTA: stage-1 survivors %.0f (live pairs %.0f), level-1 passes %.0f -> rows %.0f, level-2 passes %.0f -> rows %.0f, "
+                          "exact passes %.0f, pairs %.0f in %.0f rounds, insert candidates %.0f; warp-0 clocks level 1/2/3: %.0f %.0f %.0f\n",
+                  sc[0] / n_cta, sc[9] / n_cta, sc[1] / n_cta, sc[2] / n_cta, sc[3] / n_cta, sc[4] / n_cta, sc[5] / n_cta, sc[6] / n_cta, sc[7] / n_cta,
+                  sc[8] / n_cta, sc[13] / n_cta, sc[14] / n_cta, sc[15] / n_cta);
       }
       launches++;
       if (record && q0 + qb >= nq) CU(cudaEventRecord(h->ev[3], st));
@@ -600,7 +740,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       CU(launch_merge_keys((const uint64_t *)h->w_keys.p, k, (int64_t)out_slots * k, out_slots, qb, k, want_sqrt ? 1 : 0, 0,
                            d_labels ? d_labels + (size_t)q0 * k : nullptr, d_dists ? (void *)(d_dists + (size_t)q0 * k) : nullptr,
                            d_keys ? d_keys + (size_t)q0 * k : nullptr, ti ? h->d_id_map : nullptr, h->id_base,
-                           (uint64_t *)h->w_scratch.p, st, ti ? (const int32_t *)h->w_perm.p : nullptr));
+                           (uint64_t *)h->w_scratch.p, st, (ti || ordered) ? (const int32_t *)h->w_perm.p : nullptr));
       launches += out_slots > 16 ? 2 : 1;
     }
     if (record) { CU(cudaEventRecord(h->ev[4], st)); h->timed = true; }
@@ -842,7 +982,8 @@ void vaqgpu_destroy(vaqgpu_t *h) {
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_bounds);
   cudaFree(h->d_rowid);
-  for (DevBuf *b : {&h->w_vis, &h->w_near, &h->w_perm, &h->w_qperm, &h->w_tmask, &h->w_lsrc, &h->w_lscratch, &h->w_dbg, &h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
+  cudaFree(h->d_oc_centres_t); cudaFree(h->d_oc_start); cudaFree(h->d_oc_size);
+  for (DevBuf *b : {&h->w_vis, &h->w_near, &h->w_perm, &h->w_qperm, &h->w_tmask, &h->w_rot, &h->w_lsrc, &h->w_lscratch, &h->w_dbg, &h->w_lut16, &h->w_scale, &h->w_thr, &h->w_q, &h->w_qproj, &h->w_lut, &h->w_keys, &h->w_scratch, &h->w_ranges, &h->w_nranges, &h->w_stage,
                     &h->w_labels, &h->w_dists, &h->w_outkeys, &h->w_cdf, &h->w_x})
     b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
