@@ -264,9 +264,9 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
   // A CTA that starts without bounds has to score everything it sees exactly.  Each lane scores a few sample
   // rows of the chunk for all eight queries from the fp16 tables and keeps its minimum per query.  Error budget:
   // e16 = RZ_fp16(scale * entry) loses < 2^-10 relative on normal values and < 2^-24 absolute on subnormal ones
-  // (scaled entries below 2^-14), the half2 sums lose at most (1+2^-11)^M relative, so
-  //     (acc * (1 + 1/16) + M * 2^-24) / scale
-  // is an UPPER bound of the row's distance (M <= 64: 1.001 * 1.032 < 1.0625).  The lanes' sample rows are
+  // (scaled entries below 2^-14), the M - 1 half2 additions (round to nearest) lose at most (1 - 2^-11)^(M-1) relative, so
+  //     (acc * (1 + (M + 3) * 2^-11) + M * 2^-24) / scale
+  // is an UPPER bound of the row's distance (M <= 64: (1 - 2^-11)^-63 * (1 + 2^-10) = 1.0323 < 1.0327).  The lanes' sample rows are
   // distinct, so the k-th smallest of the per-lane minima is the upper bound of k distinct rows' distances, hence
   // bounds the k-th best distance of the chunk.
   // Sample rows per lane: at most a quarter of the chunk.  (A smaller sample on short chunks was measured slower: the
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
       }
       if (lane == 0 && lo < 0x7C00u) {
         const float x = __half2float(__ushort_as_half((unsigned short)lo));
-        const float ub = (x * (1.f + 1.f / 16.f) + (float)M * 5.9604645e-8f) / scale_s[warp] * (1.f + 1e-6f) + 1e-30f;
+        const float ub = (x * (1.f + (float)(M + 3) * 4.8828125e-4f) + (float)M * 5.9604645e-8f) / scale_s[warp] * (1.f + 1e-6f) + 1e-30f;
         if (ub < 3.0e38f) {
           publish_bound(warp, __float_as_uint(ub));
           publish_global_bound(a.thr_global, a.peers, bound_index(warp), __float_as_uint(ub));      // a valid bound for every chunk and shard
@@ -574,48 +574,77 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
         if (to_q2) q2n += __popc(m); else q3n += __popc(m);
         STAT(level == 1 ? 2 : 4, lane == 0 ? __popc(m) : 0);
       } else {
-#ifdef VAQGPU_OLD_EXACT
-        // exact distances, one (row, query) pair per lane and pass, until every lane's mask is empty
-        while (__any_sync(0xffffffffu, mask != 0)) {
-          const bool act = mask != 0;
-          const int t = act ? (__ffs(mask) - 1) : 0;
-          mask &= mask - 1;
-          const float thr = __uint_as_float(*reinterpret_cast<volatile uint32_t *>(thr_f + t));
-          widx = -2;
-          float dist = 0.f;
-          bool alive = true;
-          for (int g = 0; g < M; g += 4) {
-            float dism = 0.f;
+        // exact distances: four (row, query) pairs per round, eight lanes each.  Lane j of a pair's group takes the
+        // subspaces 4j .. 4j+3 (and 4(j+8) .., for M > 32): code and table entry of each are fetched independently — all
+        // of a pair's gathers are in flight together (one L2 / DRAM round trip; a lane-per-pair loop has M/4 dependent
+        // ones) — and summed in the reference's order and grouping: dism = ((l0+l1)+l2)+l3 inside the lane, dist += dism
+        // serially over the lanes of the group (VAQ.cpp:1741-1748).  Insertion stays one pair at a time (the whole warp
+        // shifts the list).
+        const int sub = lane >> 3, l8 = lane & 7;
+        unsigned pend = __ballot_sync(0xffffffffu, mask != 0);
+        while (pend) {
+          int my_src = -1, my_t = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const int f = g + j;
-              if (f < M) dism += __ldg(g32 + (a.lay.foff[f] + field_code(f)) * T8 + t);
+          for (int sl = 0; sl < 4; sl++) {
+            if (pend) {          // warp-uniform
+              const int src = __ffs(pend) - 1;
+              const unsigned msrc = __shfl_sync(0xffffffffu, mask, src);
+              if (lane == src) mask &= mask - 1;
+              if ((msrc & (msrc - 1u)) == 0u) pend &= pend - 1u;          // that was the last live query of this row
+              if (sub == sl) { my_src = src; my_t = __ffs(msrc) - 1; }
             }
-            dist += dism;
-            if (__all_sync(0xffffffffu, !act || (dist > thr))) { alive = false; break; }
           }
-          if (!alive) continue;
-          // keys carry the ORIGINAL row index (the storage order is conflict-aware, layout.cu): canonical (distance, id) order
-          const uint64_t key = act ? make_key_f32(dist, a.rowid ? (int32_t)__ldg(a.rowid + row) : (int32_t)row) : kEmptyKey;
-          const uint64_t kth0 = act ? *reinterpret_cast<volatile uint64_t *>(lists + (size_t)t * k + (k - 1)) : 0ull;
-          unsigned m = __ballot_sync(0xffffffffu, key < kth0);
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint64_t kk = __shfl_sync(0xffffffffu, key, src);
-            const int tt = __shfl_sync(0xffffffffu, t, src);
-            volatile uint64_t *lst = lists + (size_t)tt * k;
+          const bool valid = my_src >= 0;
+          const int64_t prow = row_base + (__shfl_sync(0xffffffffu, e, valid ? my_src : 0) >> 8);
+          const uint32_t *prp = codes32 + (((size_t)(prow >> 5) * W) * kTileRows + (prow & 31)) * 4;
+          int32_t rid = (int32_t)prow;
+          if (valid && l8 == 0 && a.rowid) rid = (int32_t)__ldg(a.rowid + prow);          // in flight with the gathers
+          STAT(6, valid && l8 == 0 ? 1 : 0); STAT(7, lane == 0 ? 1 : 0);
+          float dist = 0.f;
+          for (int g0 = 0; g0 < M; g0 += 32) {          // 8 groups of 4 subspaces per round
+            float dism = 0.f;
+            if (valid) {
+              float v[4];
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const int f = g0 + 4 * l8 + j;
+                v[j] = 0.f;
+                if (f < M) {
+                  const uint32_t meta = a.lay.fmeta[f];
+                  const uint32_t code = __funnelshift_r(__ldg(prp + a.lay.fw_lo[f]), __ldg(prp + a.lay.fw_hi[f]), meta & 31u) & (meta >> 16);
+                  v[j] = __ldg(g32 + (size_t)(a.lay.foff[f] + code) * T8 + my_t);
+                }
+              }
+              dism = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), v[2]), v[3]);          // a partial last group adds exact zeros
+            }
+            const int ng = min(8, (M - g0 + 3) >> 2);
+            for (int j = 0; j < ng; j++) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dism, (sub << 3) + j));
+          }
+          // insertion, one pair at a time: every decision is taken by one observer and broadcast (other warps lower the
+          // bounds and the lists concurrently, and the lanes meet again in full-mask shuffles)
+#pragma unroll 1
+          for (int sl = 0; sl < 4; sl++) {
+            const int t = __shfl_sync(0xffffffffu, valid ? my_t : -1, sl << 3);
+            if (t < 0) break;          // slots fill in order
+            const float d = __shfl_sync(0xffffffffu, dist, sl << 3);
+            const int32_t id = __shfl_sync(0xffffffffu, rid, sl << 3);
+            const float thr = __uint_as_float(__shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(thr_f + t), 0));
+            if (d > thr) continue;
+            // keys carry the ORIGINAL row index (the storage order is conflict-aware, layout.cu): canonical (distance, id) order
+            const uint64_t kk = make_key_f32(d, id);
+            volatile uint64_t *lst = lists + (size_t)t * k;
             {
               uint64_t c = lst[k - 1];
-              c = __shfl_sync(0xffffffffu, c, 0);      // one observer: the decision must be warp-uniform
+              c = __shfl_sync(0xffffffffu, c, 0);
               if (!(kk < c)) continue;
             }
+            STAT(8, lane == 0 ? 1 : 0);
             // take the query's list lock; give up as soon as the list has moved past this candidate
             int got = 0;
             if (lane == 0) {
               while (true) {
                 if (!(kk < lst[k - 1])) break;
-                if (atomicCAS(locks + tt, 0u, 1u) == 0u) { got = 1; break; }
+                if (atomicCAS(locks + t, 0u, 1u) == 0u) { got = 1; break; }
                 __nanosleep(100);
               }
             }
@@ -626,84 +655,15 @@ __global__ void __launch_bounds__(TPI == 2 ? 512 : 1024, 1) adc_filter16_scan_ke
             __syncwarp();
             if (lane == 0) {
               __threadfence_block();
-              atomicExch(locks + tt, 0u);
+              atomicExch(locks + t, 0u);
               if (kth != before && kth != kEmptyKey) {
                 const uint32_t bits = (uint32_t)(kth >> 32);
-                publish_bound(tt, bits);
-                publish_global_bound(a.thr_global, a.peers, bound_index(tt), bits);
+                publish_bound(t, bits);
+                publish_global_bound(a.thr_global, a.peers, bound_index(t), bits);
               }
             }
           }
         }
-#else
-        // exact distances, one (row, query) pair at a time with the lanes over the subspaces: every lane fetches the
-        // code of its subspace and the table entry, all M gathers are in flight together (one L2 / DRAM round trip per
-        // pair: a lane-per-pair loop has M/4 dependent ones), then the sum is formed in the reference's order and
-        // grouping — dism = ((l0+l1)+l2)+l3 inside each quad of lanes, dist += dism serially over the quads.
-        unsigned pend = __ballot_sync(0xffffffffu, mask != 0);
-        while (pend) {
-          const int src = __ffs(pend) - 1;
-          const unsigned msrc = __shfl_sync(0xffffffffu, mask, src);
-          const int t = __ffs(msrc) - 1;
-          if (lane == src) mask &= mask - 1;
-          if ((msrc & (msrc - 1u)) == 0u) pend &= pend - 1u;          // that was the last live query of this row
-          const int64_t prow = row_base + (__shfl_sync(0xffffffffu, e, src) >> 8);
-          const uint32_t *prp = codes32 + (((size_t)(prow >> 5) * W) * kTileRows + (prow & 31)) * 4;
-          STAT(6, lane == 0 ? 1 : 0); STAT(7, lane == 0 ? 1 : 0);
-          float dist = 0.f;
-          for (int f0 = 0; f0 < M; f0 += 32) {
-            const int f = f0 + lane;
-            float v = 0.f;
-            if (f < M) {
-              const uint32_t meta = a.lay.fmeta[f];
-              const uint32_t code = __funnelshift_r(__ldg(prp + a.lay.fw_lo[f]), __ldg(prp + a.lay.fw_hi[f]), meta & 31u) & (meta >> 16);
-              v = __ldg(g32 + (size_t)(a.lay.foff[f] + code) * T8 + t);
-            }
-            // quads: lane 4g ends up with ((l0 + l1) + l2) + l3 (a partial last quad adds exact zeros)
-            float dism = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1));
-            dism = __fadd_rn(dism, __shfl_down_sync(0xffffffffu, v, 2));
-            dism = __fadd_rn(dism, __shfl_down_sync(0xffffffffu, v, 3));
-            const int ng = min(8, (M - f0 + 3) >> 2);
-            for (int g = 0; g < ng; g++) dist = __fadd_rn(dist, __shfl_sync(0xffffffffu, dism, 4 * g));
-          }
-          // one observer per decision: other warps lower the bounds and lists concurrently, and every branch below
-          // must be warp-uniform (the lanes meet again in full-mask shuffles)
-          const float thr = __uint_as_float(__shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(thr_f + t), 0));
-          if (dist > thr) continue;
-          // keys carry the ORIGINAL row index (the storage order is conflict-aware, layout.cu): canonical (distance, id) order
-          const uint64_t kk = make_key_f32(dist, a.rowid ? (int32_t)__ldg(a.rowid + prow) : (int32_t)prow);
-          volatile uint64_t *lst = lists + (size_t)t * k;
-          {
-            uint64_t c = lst[k - 1];
-            c = __shfl_sync(0xffffffffu, c, 0);      // one observer: the decision must be warp-uniform
-            if (!(kk < c)) continue;
-          }
-          STAT(8, lane == 0 ? 1 : 0);
-          // take the query's list lock; give up as soon as the list has moved past this candidate
-          int got = 0;
-          if (lane == 0) {
-            while (true) {
-              if (!(kk < lst[k - 1])) break;
-              if (atomicCAS(locks + t, 0u, 1u) == 0u) { got = 1; break; }
-              __nanosleep(100);
-            }
-          }
-          got = __shfl_sync(0xffffffffu, got, 0);
-          if (!got) continue;
-          const uint64_t before = lst[k - 1];
-          const uint64_t kth = warp_list_insert(lst, k, kk, lane);
-          __syncwarp();
-          if (lane == 0) {
-            __threadfence_block();
-            atomicExch(locks + t, 0u);
-            if (kth != before && kth != kEmptyKey) {
-              const uint32_t bits = (uint32_t)(kth >> 32);
-              publish_bound(t, bits);
-              publish_global_bound(a.thr_global, a.peers, bound_index(t), bits);
-            }
-          }
-        }
-#endif
       }
 #ifdef VAQGPU_STATS
       st_clk[level] += clock64() - st_t0;

@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(kPlanWarps * 32) layout_plan_kernel(const uint
   while (slot < n) {
     uint32_t occ = 0u;        // residues the group already holds (one-hot per field)
     unsigned used = 0u;       // buckets already taken by this group
-    for (int m = 0; m < 8 && slot < n; m++) {
+    // a group fills one quarter-warp of the scan: 8 storage rows aligned to 8 — a window that starts off that
+    // alignment (cluster windows) begins with a short group
+    const int gsz = 8 - (int)((base + slot) & 7);
+    for (int m = 0; m < gsz && slot < n; m++) {
       // bucket: the fullest one this group has not used yet; when none is left, the fullest one
       int best_j = -1, best_n = 0;
 #pragma unroll
