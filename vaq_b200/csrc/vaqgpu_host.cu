@@ -380,8 +380,8 @@ int restore_layout(vaqgpu_index *h, cudaStream_t st);
 // The reference has no counterpart; the answer of a search does not depend on it (keys carry rowid).
 int build_scan_order(vaqgpu_index *h, cudaStream_t st, std::vector<int64_t> &cl_start, std::vector<int64_t> &cl_size) {
   const int64_t n = h->n_rows;
-  int C = 16;
-  while (C < 256 && (int64_t)C * 2048 < n) C *= 2;
+  int C = 16;          // ~2000 rows per cluster, 16..64 clusters (measured flat between 32 and 256 at 1 M rows; fewer clusters plan faster)
+  while (C < 64 && (int64_t)C * 2048 < n) C *= 2;
   C = tune_knob("order_c", C);
   const int seg = std::min(h->M, std::max(1, 16 / std::max(1, h->L)));          // ~16 leading dimensions
   const int iters = 6;

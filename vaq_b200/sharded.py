@@ -143,10 +143,22 @@ class ShardedVAQ:
         st = torch.cuda.current_stream().cuda_stream
         per = -(-nq // self.qgroups)
         a, b = self.query_slice(nq)
-        keys = torch.full((per, k), -1, dtype=torch.int64, device=d_queries.device)      # -1 == empty key
+        # the key lists and their gathered copy live in buffers kept between searches (no allocator traffic per search:
+        # with peer mappings in place a cudaMalloc costs milliseconds); labels / dists are fresh tensors owned by the caller
+        ck = (per, k, d_queries.device)
+        if getattr(self, "_buf_key", None) != ck:
+            self._keys = torch.empty((per, k), dtype=torch.int64, device=d_queries.device)
+            self._allk = torch.empty((self.world, per, k), dtype=torch.int64, device=d_queries.device)
+            self._buf_key = ck
+        keys, allk = self._keys, self._allk
+        keys.fill_(-1)                                              # -1 == empty key
         if b > a:
             self.index.search_keys_device(d_queries[a:b].data_ptr(), b - a, k, flags, keys.data_ptr(), st)
-        allk = allgather_keys(keys, self.group)                     # [world][per][k], rank = qg * R + r
+        if self.world == 1:
+            allk.copy_(keys.view(1, per, k))
+        else:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(allk.view(self.world * per, k), keys, group=self.group)      # [world][per][k], rank = qg * R + r
         labels = torch.empty((self.qgroups * per, k), dtype=torch.int32, device=d_queries.device)
         dists = torch.empty((self.qgroups * per, k), dtype=torch.float32, device=d_queries.device)
         for g in range(self.qgroups):
