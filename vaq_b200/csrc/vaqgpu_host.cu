@@ -694,7 +694,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
       for (int i = 0; i < peers.n; i++) a.peers.p[i] += q0;
       a.seed = tune_knob("seed", 1);
       a.q3_cap = std::max(1, std::min(32, tune_knob("q3cap", 32)));
-      a.seed_rows = std::max(1, std::min(16, tune_knob("spl", 4)));
+      a.seed_rows = std::max(1, std::min(16, tune_knob("spl", 3)));
       a.rowid = h->d_rowid;
       if (ti) {
         a.tile_cl = h->d_tile_cl; a.cl_start = h->d_cl_start; a.tmask = (const uint8_t *)h->w_tmask.p; a.C = h->C;
@@ -755,6 +755,11 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
     const int threads = tune_knob("threads", 1024);
     int T = nq >= 8 ? 8 : (nq >= 3 ? 4 : nq);
     T = std::min(T, tune_knob("T", 8));
+    // Tables that do not fit for T queries.  T > 1 only with every table resident: with tables spilled, a wider tile
+    // keeps fewer of the leading tables in shared memory, and stage-1 gathers from L2 cost far more than the extra
+    // passes over the rows (measured, GIST1M shape 1 K queries: T = 1 / 2 / 4 / 8 -> 15.3 / 23.8 / 33.1 / 35.6 ms;
+    // the reference's min2/max13 SIFT1M setting, 10 K queries: 86 / 103 / 113 / 172 ms).  VAQGPU_TUNE=spillT=n overrides.
+    const int spill_T = std::min(T, tune_knob("spillT", 1));
     for (;; T >>= 1) {
       const size_t fixed = adc_filter_smem_bytes(0, T, k, threads) + 1024;
       if (fixed >= kSmemCap) {
@@ -762,7 +767,7 @@ int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, u
         continue;
       }
       const size_t budget = (kSmemCap - fixed) / (4 * (size_t)T);
-      if ((size_t)h->total_entries + 4 <= budget || T == 1) {     // T > 1 only with every table resident
+      if ((size_t)h->total_entries + 4 <= budget || T <= spill_T) {
         apply_residency(h, budget, T, lay, plan, res_floats, spill_floats);
         break;
       }
