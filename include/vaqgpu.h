@@ -100,7 +100,9 @@ int vaqgpu_row_bytes(const vaqgpu_t *h, int32_t *bytes);
 int vaqgpu_get_codes_u16(vaqgpu_t *h, int64_t row0, int64_t n, uint16_t *out);
 
 /* Storage order of the packed matrix: out[i] = original (arrival) index of the row stored at position srow0 + i.
- * The library re-orders rows inside windows of 4096 so that the eight rows a quarter-warp gathers for hit different
+ * Before the first search the library groups the rows of an index of 32 K .. 8 M rows by a coarse clustering of their
+ * leading subspaces (scan order: a query tile starts at the rows nearest to it, vaqgpu_host.cu build_scan_order) and
+ * re-orders rows inside windows of at most 4096 so that the eight rows a quarter-warp gathers for hit different
  * shared-memory banks (csrc/layout.cu); ids, codes and results are always expressed in the original order — this
  * call exists for diagnostics and tests. */
 int vaqgpu_get_row_order(vaqgpu_t *h, int64_t srow0, int64_t n, uint32_t *out);
