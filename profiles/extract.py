@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Turn .ncu-rep captures (gpurun_out/, scratch) into the small text artefacts committed here.
-usage: python profiles/extract.py <tag> <rep> [<kernel-key> <workload> <n_gpus>]"""
+usage: [NCU_ROW=i] python profiles/extract.py <tag> <rep> [<kernel-key> <workload> <n_gpus>]"""
 import csv, io, json, subprocess, sys
 from pathlib import Path
 HERE = Path(__file__).resolve().parent
 tag, rep = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+import os
+hdr, units, vals = rows[0], rows[1], rows[2 + int(os.environ.get("NCU_ROW", "0"))]      # NCU_ROW: which result of a multi-kernel report
 keep = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "lts__t_sectors_srcunit_tex_op_read.sum", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
