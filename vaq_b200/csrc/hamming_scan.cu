@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t hamming_words(const uint4 (&r)[W], const uin
 }
 
 template <int W, int QT>
-__global__ void __launch_bounds__(256, (W <= 2 ? 4 : 2)) ham_scan_kernel(const __grid_constant__ HamScanArgs a) {
+__global__ void __launch_bounds__(256, (W <= 2 ? (QT == 1 ? 6 : 4) : 2)) ham_scan_kernel(const __grid_constant__ HamScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int k = a.k;

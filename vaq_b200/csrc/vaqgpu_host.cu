@@ -1580,7 +1580,11 @@ int ham_query_impl(hamgpu_index *h, const uint64_t *d_queries, int nq, int k, in
   const int64_t n_tiles = (h->n_rows + kTileRows - 1) / kTileRows;
   const int qb_max = std::min(nq, 32768);                       // grid.y = query groups: bounded per launch
   const int qgroups = (qb_max + qt - 1) / qt;
-  const int64_t target = (int64_t)h->num_sms * 4 * 2;
+  // two waves of resident CTAs (ham_scan_kernel's launch bounds: 6 per SM for one query per pass on rows of <= 256 bits — more
+  // warps, hence more tiles in flight, where the pass is bound by load latency: 0.36 -> 0.335 ms on 64 M rows; with two
+  // queries both 6 (40 registers, spills) and 5 (47 registers) measured slower: 0.57 / 0.49 vs 0.46 ms —, 4 otherwise, 2 for wider rows)
+  const int occ = W <= 2 ? (qt == 1 ? 6 : 4) : 2;
+  const int64_t target = (int64_t)h->num_sms * occ * 2;
   int splits = (int)std::max<int64_t>(1, (target + qgroups - 1) / qgroups);
   splits = (int)std::min<int64_t>(splits, std::max<int64_t>(1, n_tiles / (nwarps * 8)));
   CU(h->w_keys.ensure((size_t)qb_max * splits * k * sizeof(uint64_t)));
