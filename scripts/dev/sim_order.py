@@ -62,12 +62,14 @@ run(ev, lambda t: np.arange(N), rand_tiles, "arrival order, random sample seed",
 live = ev.P4 < ev.final[:, None]
 print(f"{'final bounds from the start':40s}: stage-1 surviving rows per tile {np.mean([live[q].any(axis=0).mean() for _, q in rand_tiles]):.4f}   live pairs per query {live.mean():.4f}")
 
-for C_ in (64, 256):
-    segs = 4; dims = segs * m.L
-    dec = np.concatenate([m.centroids[s][codes[:, s]] for s in range(segs)], axis=1)
+import os
+SEG_LO = int(os.environ.get("SEG_LO", "0")); SEG_N = int(os.environ.get("SEG_N", "4"))
+for C_ in (64,):
+    segs = SEG_N; dims = segs * m.L
+    dec = np.concatenate([m.centroids[s][codes[:, s]] for s in range(SEG_LO, SEG_LO + segs)], axis=1)
     cent = train.kmeans(dec[rng.choice(N, 20000, replace=False)], C_, iters=10)
     a = np.concatenate([np.argmin(((dec[i:i + 8192, None, :] - cent[None]) ** 2).sum(-1), axis=1) for i in range(0, N, 8192)])
-    qd = ((Q[:, None, :dims] - cent[None]) ** 2).sum(-1)
+    qd = ((Q[:, None, SEG_LO * m.L:SEG_LO * m.L + dims] - cent[None]) ** 2).sum(-1)
     near = np.argmin(qd, axis=1)
     qorder = np.argsort(near, kind="stable")
     sel = rng.choice(NQ // 8, NT, replace=False)
@@ -80,7 +82,7 @@ for C_ in (64, 256):
     live = ev.P4 < ev.final[:, None]
     print(f"C={C_}: final bounds, grouped tiles: surviving rows per tile {np.mean([live[q].any(axis=0).mean() for _, q in tiles]):.4f}   live pairs per query {live.mean():.4f}")
     run(ev, lambda t: storage, tiles, f"C={C_} grouped tiles, storage order, random seed", lambda t: samp)
-    for P in (1, 2, 4, 8):
+    for P in (1,):
         def order_of_tile(t, P=P):
             cl = np.argsort(qd[first_q[t]])[:P]
             if P == 1:        # rotation
