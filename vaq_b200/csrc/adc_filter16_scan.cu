@@ -18,9 +18,12 @@
 //                          registers, the lower bound over groups 1-2 (level 1) / all subspaces (level 2) is
 //                          accumulated for all eight queries the same way, and the query mask shrinks.
 //   level 3 (exact)        rows that still have a query under its bound are scored EXACTLY for those queries
-//                          from the fp32 tables in global memory (L2), in the reference's order and grouping
-//                          (dism = ((l0+l1)+l2)+l3 ; dist += dism, VAQ.cpp:1741-1748).  Only these exact
-//                          distances enter the top-k lists and tighten the bounds.
+//                          from the fp32 tables in global memory (L2): four (row, query) pairs per round, eight
+//                          lanes each, in the reference's order and grouping (dism = ((l0+l1)+l2)+l3 ;
+//                          dist += dism, VAQ.cpp:1741-1748).  Only these exact distances enter the top-k lists
+//                          and tighten the bounds.
+// A query tile may start its scan anywhere in the chunk (scan order, vaqgpu_host.cu build_scan_order): the rows nearest
+// to the tile's queries first, so that the bounds are tight after the first percent of the rows.
 //
 // Exactness of the pruning.  Entries are rounded toward zero, half2 additions round to nearest: after n
 // additions the accumulated value is at most (1+2^-11)^n above the real sum of the (scaled) entries.  A pair

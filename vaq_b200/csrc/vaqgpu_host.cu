@@ -549,7 +549,10 @@ int drop_clusters(vaqgpu_index *h) {
 // Scan kernel selection (the reference dispatches TI -> EA -> HEAP, VAQ.cpp:799-840):
 //   EA / HEAP        -> adc_filter16_scan_kernel (fp16 lower-bound filter + exact scoring of the survivors), or
 //                       adc_filter_scan_kernel when eight queries' fp16 tables do not fit in shared memory
-//   TI / visit       -> adc_scan_kernel over per-query row ranges, with abandoning
+//   TI / visit       -> the same fp16 filter kernel over the visited clusters (ti_plan.cu) when the cluster ranges partition
+//                       the rows in ascending order and the tables fit; otherwise adc_scan_kernel over per-query row ranges
+//   scan order       -> EA / HEAP searches of an index grouped by coarse cluster (build_scan_order) re-group the batch
+//                       into query tiles by nearest cluster and start each tile's scan there
 //   VAQGPU_SCAN_V1   -> force adc_scan_kernel (lane-per-row; exhaustive with HEAP, warp-uniform abandoning with EA)
 int search_device_impl(vaqgpu_index *h, const float *d_queries, int nq, int k, uint32_t flags, int32_t *d_labels,
                        float *d_dists, uint64_t *d_keys, cudaStream_t st, bool record) {
