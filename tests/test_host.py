@@ -83,3 +83,40 @@ def test_shard_bounds_and_key_format():
     assert np.array_equal(i2, ids) and np.array_equal(d2, d)
     hk = make_keys_u32(np.array([3, 3, 1]), np.array([5, 4, 9]))
     assert np.argsort(hk).tolist() == [2, 1, 0]
+
+
+def test_fp16_seed_bound_is_an_upper_bound():
+    """Numerics of the fp16 filter kernel's bound seeding (csrc/adc_filter16_scan.cu): entries are round-toward-zero fp16
+    of scale * entry, summed in half precision with round-to-nearest additions in subspace order; the seed
+    (acc * (1 + (M + 3) * 2^-11) + M * 2^-24) / scale must never fall below the real distance — including subnormal and
+    zero entries and M = 64, the largest model the seeding accepts.  (numpy's float16 addition is the correctly rounded
+    sum, like HADD2.)"""
+    rng = np.random.default_rng(5)
+
+    def rz16(x):
+        h = x.astype(np.float16)
+        up = h.astype(np.float64) > x
+        h[up] = np.nextafter(h[up], np.float16(-np.inf))
+        return h
+
+    worst = 0.0
+    for M in (4, 9, 32, 64):
+        for scale_exp in (-20, -3, 0, 7, 20):
+            scale = 2.0 ** scale_exp
+            for spread in (1e-9, 1e-4, 1.0):
+                ent = (rng.random((4000, M)) ** 3 * spread * 200.0 / scale).astype(np.float32)      # scaled entries up to ~200
+                ent[:, rng.integers(0, M)] = 0.0
+                # adversarial half: entries just below the next fp16 value (round-toward-zero loses almost a whole ulp)
+                h = (ent[2000:].astype(np.float64) * scale).astype(np.float16).astype(np.float64)
+                ent[2000:] = (np.nextafter(np.nextafter(h.astype(np.float16), np.float16(np.inf)).astype(np.float32), np.float32(0)) / scale).astype(np.float32)
+                true = ent.astype(np.float64).sum(1)
+                e16 = rz16(ent.astype(np.float64) * scale)
+                acc = np.zeros(ent.shape[0], np.float16)
+                for s in range(M):
+                    acc = (acc + e16[:, s]).astype(np.float16)
+                ok = np.isfinite(acc.astype(np.float64))
+                ub = (acc.astype(np.float64) * (1.0 + (M + 3) * 2.0 ** -11) + M * 2.0 ** -24) / scale
+                assert (ub[ok] >= true[ok]).all(), (M, scale_exp, spread)
+                nz = ok & (true > 0)
+                worst = max(worst, float((true[nz] / ub[nz]).max()))
+    assert worst <= 1.0
