@@ -448,4 +448,112 @@ class BitVecEngine {
   hamgpu_t *h_ = nullptr;
 };
 
+// ---- the same two classes over the GPUs of one box (one host process, vaqgpu_sharded_* / hamgpu_sharded_*) ----------
+// Rows are appended in order and land in contiguous blocks of ceil(n_rows_total / n_gpus) per device; every
+// device scans its block for all queries, the shards exchange their running k-th-best bounds through peer memory, and
+// one ncclAllGather + device merge of the shard-local key lists gives the answer of a single index, bit for bit (the
+// reference's precedent for merging partial answers: BitVecEngine.cpp:1599-1611).  n_rows_total fixes the block size and
+// must be known before the first row arrives.
+class ShardedVAQ {
+ public:
+  int mMethods = VAQ::Heap;                  // VAQ::EA or VAQ::Heap (TI: per-shard handles, vaqgpu_sharded_shard)
+  int mSubsLen = 0, mHighestSubs = 0;
+
+  ShardedVAQ(int n_gpus, int64_t n_rows_total, const int *dev_ids = nullptr)
+      : n_gpus_(n_gpus), n_total_(n_rows_total), dev_ids_(dev_ids ? std::vector<int>(dev_ids, dev_ids + n_gpus) : std::vector<int>()) {}
+  ~ShardedVAQ() { vaqgpu_sharded_destroy(h_); }
+  ShardedVAQ(const ShardedVAQ &) = delete;
+  ShardedVAQ &operator=(const ShardedVAQ &) = delete;
+
+  // what VAQ::train produced, as in VAQ::loadModel above
+  void loadModel(int subsLen, int highestSubs, const int *bitsAlloc, const float *centroidsPerSubs, const float *eigReal) {
+    vaqgpu_sharded_destroy(h_);
+    h_ = nullptr;
+    mSubsLen = subsLen;
+    mHighestSubs = highestSubs;
+    vaqgpu_model_desc d;
+    d.D = subsLen * highestSubs; d.M = highestSubs; d.L = subsLen;
+    d.bits = bitsAlloc; d.centroids = centroidsPerSubs; d.eig_real = eigReal;
+    check(vaqgpu_sharded_create(&d, n_gpus_, dev_ids_.empty() ? nullptr : dev_ids_.data(), n_total_, &h_));
+    has_eig_ = eigReal != nullptr;
+  }
+  // mCodebook rows [n x mHighestSubs] uint16, appended in arrival order (may be called in pieces)
+  void setCodebook(const uint16_t *codes, int64_t n) { check(vaqgpu_sharded_add_codes_u16(need(), codes, n)); }
+  // VAQ::encode (VAQ.cpp:663) on the devices: projected rows, appended in arrival order
+  void encode(const float *XTrainProjected, int64_t n) { check(vaqgpu_sharded_encode_add(need(), XTrainProjected, n)); }
+  int numShards() const {
+    int32_t g = 0;
+    if (h_) check(vaqgpu_sharded_num_shards(h_, &g));
+    return g;
+  }
+  // VAQ::search (VAQ.cpp:776-847): XTest raw [nq x D] when the model has eigenvectors, else projected
+  LabelDistVecF search(const float *XTest, int nq, int k, bool /*verbose*/ = false) {
+    LabelDistVecF ret;
+    ret.labels.resize((size_t)nq * k);
+    ret.distances.resize((size_t)nq * k);
+    const uint32_t flags = (has_eig_ ? 0u : VAQGPU_PROJECTED) | ((mMethods & VAQ::EA) ? VAQGPU_EA : VAQGPU_HEAP);
+    check(vaqgpu_sharded_search(need(), XTest, nq, k, flags, ret.labels.data(), ret.distances.data()));
+    return ret;
+  }
+#ifdef VAQGPU_HAVE_EIGEN
+  void encode(const RowMatrixXf &XTrain) { encode(XTrain.data(), (int64_t)XTrain.rows()); }
+  LabelDistVecF search(const RowMatrixXf &XTest, const int k, bool verbose = false) {
+    if ((int)XTest.cols() != mSubsLen * mHighestSubs) throw std::runtime_error("vaqgpu::ShardedVAQ::search: XTest must have M*L columns");
+    return search(XTest.data(), (int)XTest.rows(), k, verbose);
+  }
+#endif
+
+ private:
+  vaqgpu_sharded_t *need() {
+    if (!h_) throw std::runtime_error("vaqgpu::ShardedVAQ: loadModel first");
+    return h_;
+  }
+  int n_gpus_;
+  int64_t n_total_;
+  std::vector<int> dev_ids_;
+  vaqgpu_sharded_t *h_ = nullptr;
+  bool has_eig_ = false;
+};
+
+class ShardedBitVecEngine {
+ public:
+  const int N;
+  const int actBitVLen;
+  ShardedBitVecEngine(int _N, int n_gpus, int64_t n_rows_total, const int *dev_ids = nullptr) : N(_N), actBitVLen((_N + 63) / 64) {
+    check(hamgpu_sharded_create(_N, n_gpus, dev_ids, n_rows_total, &h_));
+  }
+  ~ShardedBitVecEngine() { hamgpu_sharded_destroy(h_); }
+  ShardedBitVecEngine(const ShardedBitVecEngine &) = delete;
+  ShardedBitVecEngine &operator=(const ShardedBitVecEngine &) = delete;
+
+  // BitVecEngine::loadBitV / appendBitV: rows appended in arrival order
+  void appendBitV(const bitvectors &bv) {
+    std::vector<uint64_t> flat = flatten(bv);
+    check(hamgpu_sharded_add(h_, flat.data(), (int64_t)bv.size()));
+  }
+  // BitVecEngine::query / queryParallel
+  std::vector<std::vector<IdxDistPair>> query(const bitvectors &queries, int k, int /*method*/ = BitVecEngine::Sort) const {
+    const int nq = (int)queries.size();
+    std::vector<uint64_t> flat = flatten(queries);
+    std::vector<int32_t> idx((size_t)nq * k);
+    std::vector<uint32_t> dist((size_t)nq * k);
+    check(hamgpu_sharded_query(h_, flat.data(), nq, k, idx.data(), dist.data()));
+    std::vector<std::vector<IdxDistPair>> out((size_t)nq);
+    for (int q = 0; q < nq; q++)
+      for (int j = 0; j < k && idx[(size_t)q * k + j] >= 0; j++) out[(size_t)q].push_back(IdxDistPair{idx[(size_t)q * k + j], dist[(size_t)q * k + j]});
+    return out;
+  }
+
+ private:
+  std::vector<uint64_t> flatten(const bitvectors &bv) const {
+    std::vector<uint64_t> flat(bv.size() * (size_t)actBitVLen, 0);
+    for (size_t i = 0; i < bv.size(); i++) {
+      if ((int)bv[i].size() != actBitVLen) throw std::runtime_error("bit vector length does not match the engine");
+      for (int w = 0; w < actBitVLen; w++) flat[i * (size_t)actBitVLen + (size_t)w] = bv[i][(size_t)w];
+    }
+    return flat;
+  }
+  hamgpu_sharded_t *h_ = nullptr;
+};
+
 }  // namespace vaqgpu

@@ -100,6 +100,26 @@ int main(int argc, char **argv) {
     }
     if (!kat_ok) { fprintf(stderr, "BitVecEngine known-answer mismatch\n"); return 4; }
 
+    // the sharded classes over as many GPUs as the box has (at most 2 here): same answers as the single index, bit for bit
+    {
+      int n_dev = 0;
+      vaqgpu::check(vaqgpu_device_count(&n_dev));
+      const int G = n_dev >= 2 ? 2 : 1;
+      vaqgpu::ShardedVAQ sv(G, n);
+      sv.mMethods = vaqgpu::VAQ::EA;
+      sv.loadModel(L, M, bits.data(), centroids.data(), has_eig ? eig.data() : nullptr);
+      sv.setCodebook(codes.data(), n / 3);                                   // pieces that straddle the shard boundary
+      sv.setCodebook(codes.data() + (size_t)(n / 3) * M, n - n / 3);
+      vaqgpu::LabelDistVecF sa = sv.search(queries.data(), nq, k);
+      if (sv.numShards() != G || sa.labels != ea.labels || sa.distances != ea.distances) { fprintf(stderr, "ShardedVAQ differs from VAQ\n"); return 4; }
+      vaqgpu::ShardedBitVecEngine se(64, G, 5);
+      vaqgpu::bitvectors bv = {{0x327B23C66B8B4567ull}, {0x19495CFF74B0DC51ull}, {0xFFFFFFF0FFFFFFFFull}, {0x00000000F0000000ull}, {0x000000000000000Full}};
+      se.appendBitV({bv[0], bv[1]});
+      se.appendBitV({bv[2], bv[3], bv[4]});
+      auto r = se.query({bv[1]}, 3);
+      if (!(r.size() == 1 && r[0].size() == 3 && r[0][0].idx == 1 && r[0][1].idx == 3 && r[0][2].idx == 2)) { fprintf(stderr, "ShardedBitVecEngine known-answer mismatch\n"); return 4; }
+    }
+
     FILE *o = fopen(argv[2], "wb");
     fwrite(ea.labels.data(), sizeof(int), ea.labels.size(), o);
     fwrite(ea.distances.data(), sizeof(float), ea.distances.size(), o);
