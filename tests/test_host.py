@@ -120,3 +120,40 @@ def test_fp16_seed_bound_is_an_upper_bound():
                 nz = ok & (true > 0)
                 worst = max(worst, float((true[nz] / ub[nz]).max()))
     assert worst <= 1.0
+
+
+def test_fp16_filter_margins_never_drop_a_pair_under_the_bound():
+    """Numerics of the fp16 lower-bound filter (csrc/adc_filter16_scan.cu, header comment): a (row, query) pair is dropped
+    when its half-precision partial sum exceeds RU_fp16(thr * scale * (1 + m)), m = 2^-9 after the 4 fields of stage 1,
+    2^-7 after 8 (level 1), 2^-5 after up to 32 (level 2, M <= 32), 2^-3 beyond.  A dropped pair's real partial sum — and
+    with it the distance the reference computes — must exceed thr.  Checked on sums sitting right at the bound."""
+    rng = np.random.default_rng(11)
+
+    def rz16(x):
+        h = x.astype(np.float16)
+        up = h.astype(np.float64) > x
+        h[up] = np.nextafter(h[up], np.float16(-np.inf))
+        return h
+
+    def ru16(x):
+        h = x.astype(np.float16)
+        dn = h.astype(np.float64) < x
+        h[dn] = np.nextafter(h[dn], np.float16(np.inf))
+        return h
+
+    for nf, m in ((4, 2.0 ** -9), (8, 2.0 ** -7), (32, 2.0 ** -5), (64, 2.0 ** -3)):
+        for scale_exp in (-12, 0, 9):
+            scale = 2.0 ** scale_exp
+            n = 20000
+            ent = (rng.random((n, nf)) ** 2 * 300.0 / nf / scale).astype(np.float32)
+            true = ent.astype(np.float64).sum(1)
+            # thresholds around each row's own sum: the decisions that matter are the near-ties
+            thr = (true * (1.0 + (rng.random(n) - 0.8) * 4.0 * m)).astype(np.float32)
+            e16 = rz16(ent.astype(np.float64) * scale)
+            acc = e16[:, 0].copy()
+            for s in range(1, nf):
+                acc = (acc + e16[:, s]).astype(np.float16)
+            bound = ru16((thr.astype(np.float32) * np.float32(scale) * np.float32(1.0 + m)).astype(np.float64))
+            dropped = acc.astype(np.float64) > bound.astype(np.float64)
+            assert dropped.any() and (~dropped).any()
+            assert (true[dropped] > thr[dropped].astype(np.float64)).all(), (nf, scale_exp)
